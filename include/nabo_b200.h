@@ -1,0 +1,150 @@
+/* nabo_b200 - C ABI of the B200-native nabo cell-projection hot path.
+ *
+ * Drop-in boundary.  The reference (parashardhapola/nabo 0.4.1) has
+ * no FFI: its hot path is five module-level Python operators called by
+ * Dataset / Mapping / Graph.  Each entry point below replaces one of them and is
+ * what a ctypes binding inside the reference would call.
+ * File:line citations are relative to the reference checkout.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns every buffer, including workspace (query the size first);
+ *   - every call is asynchronous on `stream` (a cudaStream_t, passed as void*);
+ *   - return value: 0 = OK, <0 = invalid argument (NABO_E*), >0 = cudaError_t;
+ *     nabo_last_error() returns a thread-local message.  No exceptions, no global
+ *     state, no host fallback: without a CUDA device every compute call fails.
+ *   - matrices are row-major; `ld*` is the row stride in elements.
+ *   - neighbour order everywhere: ascending distance, ties by ascending index,
+ *     NaN distances and masked reference cells last (numpy.ma.argsort semantics of
+ *     nabo/_mapping.py:135-146; the reference's own tie order is unspecified).
+ */
+#ifndef NABO_B200_H
+#define NABO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NABO_ABI_VERSION 1
+
+#define NABO_EINVAL (-1)      /* bad argument                                  */
+#define NABO_EWORKSPACE (-2)  /* workspace missing or too small                */
+#define NABO_EUNSUPPORTED (-3)/* shape outside what the kernels are built for  */
+
+/* metric ids.  Reference dispatch: euclidean when the query set IS the reference
+ * (intra_ref), modified Canberra otherwise (nabo/_mapping.py:119-124, 433-440).
+ * Cosine and query!=reference Euclidean are extensions (BASELINE.json). */
+#define NABO_EUCLIDEAN 0
+#define NABO_MOD_CANBERRA 1
+#define NABO_COSINE 2
+
+/* kNN engines */
+#define NABO_MODE_EXACT 0 /* FP64 brute force in the reference's arithmetic order */
+#define NABO_MODE_FAST 1  /* tensor-core / FP32 candidate pass + exact FP64 re-rank
+                             + certificate, exact fallback for uncertified rows   */
+
+int nabo_abi_version(void);
+const char* nabo_last_error(void);
+/* 0 when a compute-capability 10.x device is current; fills sm count if non-NULL. */
+int nabo_device_check(int* sm_count);
+
+/* ---- (1) full distance tiles: replace the two numba kernels -------------------
+ * _euclidean_dist(x, y, d)            nabo/_mapping.py:16-26
+ * _mod_canberra_dist(x, y, d, f)      nabo/_mapping.py:29-45
+ * Caller allocates d (m x n, row stride ldd); filled in place; bit-identical to
+ * the numba kernels (sequential ascending-k FP64, no FMA contraction). */
+int nabo_euclidean_dist(const double* x, int ldx, const double* y, int ldy, double* d, int ldd,
+                        int m, int n, int g, void* stream);
+int nabo_mod_canberra_dist(const double* x, int ldx, const double* y, int ldy, double* d, int ldd,
+                           int m, int n, int g, double f, void* stream);
+int nabo_cosine_dist(const double* x, int ldx, const double* y, int ldy, double* d, int ldd,
+                     int m, int n, int g, void* stream);
+
+/* ---- (2) fused distance + per-query top-k: replaces _calc_dist ------------------
+ * nabo/_mapping.py:48-148, restricted to what _calc_snn consumes ([:k] of every
+ * sorted row, :190/:193): the N x M matrix is never written.
+ *   q (n_query x g), r (n_ref x g)  FP64 PCA coordinates (first use_comps columns)
+ *   ref_mask   n_ref bytes, non-zero = ignore_ref_cells member (sorts last) or NULL
+ *   drop_first non-zero = reference<->reference rows: drop the first sorted
+ *              element ("self", :141-142) and return the next k
+ *   idx_offset added to every output index (reference-sharded mode)
+ *   out_idx (n_query x k) int32, out_dist (n_query x k) FP64 (NaN for masked /
+ *   missing entries, idx -1 when fewer than k references exist)
+ *   stats_host optional int64[4]: {rows re-ranked, rows sent to exact fallback,
+ *              candidates kept per row, 0}; filled only if non-NULL (forces a sync)
+ */
+size_t nabo_knn_workspace_bytes(int n_query, int n_ref, int g, int k, int metric, int mode);
+int nabo_knn(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
+             int k, int metric, double dist_factor, const uint8_t* ref_mask, int drop_first,
+             int idx_offset, int mode, int32_t* out_idx, double* out_dist, void* workspace,
+             size_t workspace_bytes, int64_t* stats_host, void* stream);
+
+/* Exact re-rank of caller-supplied candidates (cand: n_query x n_cand int32 LOCAL
+ * reference indices, -1 = empty) in the reference's arithmetic; writes the best k. */
+int nabo_rerank_exact(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref,
+                      int g, int k, int metric, double dist_factor, const uint8_t* ref_mask,
+                      int drop_first, int idx_offset, const int32_t* cand, int n_cand,
+                      int32_t* out_idx, double* out_dist, void* stream);
+
+/* ---- (3) candidate merge for the reference-sharded mode -------------------------
+ * idx/dist: n_shards blocks of (n_query x k), shard-major (the layout an NCCL
+ * all-gather produces); result = the k best per query by (dist, idx). */
+int nabo_merge_topk(const int32_t* idx, const double* dist, int n_shards, int n_query, int k,
+                    int32_t* out_idx, double* out_dist, void* stream);
+
+/* ---- (4) SNN neighbour weights: replaces _calc_snn ------------------------------
+ * nabo/_mapping.py:151-200.  counts[t][j] = |set(tgt_knn[t]) & set(ref_knn[tgt_knn[t][j]])|
+ * weights[t][j] = lut[counts] with lut[s] = round(s / (2(k-1) - s), 2) built on
+ * the host with Python's round() (so weights are bit-exact); an edge exists iff
+ * counts > 0 (:195).  Negative indices (missing neighbours) give count 0. */
+int nabo_snn_weights(const int32_t* tgt_knn, int n_query, int k, const int32_t* ref_knn, int n_ref,
+                     int k_ref, const double* lut, uint8_t* out_counts, double* out_weights,
+                     void* stream);
+
+/* ---- (5) per-reference mapping scores: replaces Graph.get_mapping_score core ----
+ * nabo/_graph.py:643-653, 690-693.  Edges (t -> tgt_knn[t][j], weight) with
+ * counts > 0 are sorted by (reference, target) with a stable LSD radix sort and
+ * summed per reference cell IN TARGET ORDER (the reference's adjacency order), so
+ * the result is deterministic and independent of scheduling.  include (n_query
+ * bytes or NULL) selects the target subset; n_include is its size (the divisor). */
+size_t nabo_scores_workspace_bytes(int n_query, int k, int n_ref);
+int nabo_mapping_scores(const int32_t* tgt_knn, const uint8_t* counts, const double* lut,
+                        int n_query, int k, int n_ref, const uint8_t* include, int n_include,
+                        double min_weight, int weighted, double score_multiplier,
+                        double min_score, double* out_scores, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Per-target cluster vote: array form of Graph.classify_target (nabo/_graph.py:722-792).
+ * ref_labels int32 (n_ref), -1 = unlabelled; out_label -1 = na_label. */
+int nabo_classify_targets(const int32_t* tgt_knn, const uint8_t* counts, const double* lut,
+                          int n_query, int k, const int32_t* ref_labels, int n_labels,
+                          double weight_frac, int min_degree, double min_weight,
+                          int32_t* out_label, void* stream);
+
+/* ---- (6) scaling + PCA projection: replaces get_scaled_values + transform_pca ---
+ * nabo/_dataset.py:905-913 and :1028 (sklearn IncrementalPCA.transform):
+ *   a = counts as float32; z = ((a * sf_i) [float32] - mu) / sigma   [float64]
+ *   P = z @ components.T - mean @ components.T                       [float64]
+ * Dense form: counts (n_cells x ld) float32, gene_idx[G] selects/reorders columns
+ * (the reference's `goi`; -1 = gene missing in this dataset -> value 0, :909-910).
+ * CSR form: indptr int64 (n_cells+1), col int32, val float32 over ALL genes of
+ * the dataset; gene_pos[n_genes_total] = position in the model's gene order or -1.
+ * components (n_comps x G) row-major, mean (G).  out (n_cells x ldo) FP64. */
+int nabo_project_dense(const float* counts, int ld, int n_cells, const int32_t* gene_idx, int G,
+                       const float* sf, const double* mu, const double* sigma,
+                       const double* components, const double* mean, int n_comps, double* out,
+                       int ldo, void* stream);
+size_t nabo_project_csr_workspace_bytes(int G, int n_comps);
+int nabo_project_csr(const int64_t* indptr, const int32_t* col, const float* val, int n_cells,
+                     const int32_t* gene_pos, int n_genes_total, int G, const float* sf,
+                     const double* mu, const double* sigma, const double* components,
+                     const double* mean, int n_comps, double* out, int ldo, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NABO_B200_H */

@@ -1,0 +1,366 @@
+"""Array-level public API of the hot path (host side of the C ABI).
+
+Each function mirrors one reference operator (file:line in the docstrings) and
+accepts either NumPy arrays (host buffers: copied to the device through pinned
+memory, results copied back) or ``torch`` CUDA tensors (used in place, results
+stay on the device).  PyTorch is used only for device memory and streams; every
+computation is a call into ``libnabo_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import METRICS, MODE_EXACT, MODE_FAST, check, lib, require_device
+
+__all__ = ["euclidean_dist", "mod_canberra_dist", "cosine_dist", "knn", "rerank_exact", "merge_topk",
+           "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets",
+           "project", "project_csr", "map_cells", "resolve_metric"]
+
+
+# ----------------------------------------------------------------------------- helpers
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _is_host(*xs) -> bool:
+    return any(isinstance(x, np.ndarray) or (x is not None and not isinstance(x, torch.Tensor)) for x in xs
+               if x is not None)
+
+
+def _dev(x, dtype: torch.dtype, name: str = "array") -> Optional[torch.Tensor]:
+    """Device tensor of `dtype`, row-major contiguous.  Host arrays travel through pinned memory."""
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        if not x.is_cuda:
+            x = x.pin_memory().cuda(non_blocking=True)
+        if x.dtype != dtype:
+            x = x.to(dtype)
+        return x.contiguous()
+    a = np.ascontiguousarray(x)
+    t = torch.from_numpy(a)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.pin_memory().cuda(non_blocking=True)
+
+
+def _mask_dev(mask) -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    if isinstance(mask, torch.Tensor):
+        return _dev(mask.to(torch.uint8), torch.uint8)
+    return _dev(np.asarray(mask).astype(np.uint8), torch.uint8)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _out(t: torch.Tensor, host: bool):
+    return t.cpu().numpy() if host else t
+
+
+def resolve_metric(metric: Optional[str], intra_ref: bool) -> str:
+    """Reference dispatch (nabo/_mapping.py:119-124, 433-440): Euclidean when the query
+    set is the reference itself, modified Canberra otherwise; an explicit name overrides."""
+    if metric is None:
+        return "euclidean" if intra_ref else "mod_canberra"
+    if metric not in METRICS:
+        raise ValueError("ERROR: unknown metric %r (choose from %s)" % (metric, sorted(METRICS)))
+    return metric
+
+
+# ----------------------------------------------------------------------------- (1) distance tiles
+def _dist(fn_name: str, x, y, d, f: Optional[float]):
+    require_device()
+    host = _is_host(x, y, d)
+    xd, yd = _dev(x, torch.float64), _dev(y, torch.float64)
+    if xd.dim() != 2 or yd.dim() != 2 or xd.shape[1] != yd.shape[1]:
+        raise ValueError("ERROR: x and y must be 2-D with the same number of columns")
+    m, g = xd.shape
+    n = yd.shape[0]
+    if d is None:
+        dd = torch.empty((m, n), dtype=torch.float64, device=xd.device)
+    elif isinstance(d, torch.Tensor):
+        if tuple(d.shape) != (m, n) or d.dtype != torch.float64 or not d.is_contiguous() or not d.is_cuda:
+            raise ValueError("ERROR: d must be a contiguous float64 CUDA tensor of shape (%d, %d)" % (m, n))
+        dd = d
+    else:
+        if d.shape != (m, n) or d.dtype != np.float64:
+            raise ValueError("ERROR: d must be a float64 array of shape (%d, %d)" % (m, n))
+        dd = torch.empty((m, n), dtype=torch.float64, device=xd.device)
+    fn = getattr(lib(), fn_name)
+    args = [_ptr(xd), g, _ptr(yd), g, _ptr(dd), n, m, n, g]
+    if f is not None:
+        args.append(float(f))
+    args.append(C.c_void_p(_stream()))
+    check(fn(*args), fn_name)
+    if isinstance(d, np.ndarray):
+        d[...] = dd.cpu().numpy()      # the reference kernels fill the caller's buffer in place
+        return d
+    return _out(dd, host) if d is None else dd
+
+
+def euclidean_dist(x, y, d=None):
+    """``_euclidean_dist(x, y, d)`` (nabo/_mapping.py:16-26): fills ``d`` (m x n float64) in
+    place, bit-identical to the numba kernel.  ``d=None`` allocates and returns it."""
+    return _dist("nabo_euclidean_dist", x, y, d, None)
+
+
+def mod_canberra_dist(x, y, d=None, f: float = 0.25):
+    """``_mod_canberra_dist(x, y, d, f)`` (nabo/_mapping.py:29-45); x = target, y = reference."""
+    if not (float(f) > 0):
+        raise ValueError('ERROR: "dist_factor" must be a non-zero float value')
+    return _dist("nabo_mod_canberra_dist", x, y, d, f)
+
+
+def cosine_dist(x, y, d=None):
+    """Extension metric: 1 - x.y/(|x||y|), sequential FP64 (no reference counterpart)."""
+    return _dist("nabo_cosine_dist", x, y, d, None)
+
+
+# ----------------------------------------------------------------------------- (2) kNN
+def knn(q, r, k: int, metric: str = "euclidean", dist_factor: float = 0.25, ref_mask=None,
+        drop_first: bool = False, idx_offset: int = 0, mode: str = "fast", return_stats: bool = False):
+    """Fused distance + per-query top-k: what ``_calc_dist`` (nabo/_mapping.py:48-148) leaves
+    for ``_calc_snn`` to read (``[:k]`` of each sorted row), without the N x M matrix.
+
+    q (N,g), r (M,g) float64.  ``ref_mask`` (M,) bool marks ``ignore_ref_cells`` (sorted last,
+    :135-140); ``drop_first`` is the reference<->reference ``[1:]`` (:141-142).
+    Returns (idx int32 (N,k), dist float64 (N,k)) [+ stats dict]."""
+    require_device()
+    if metric not in METRICS:
+        raise ValueError("ERROR: unknown metric %r" % (metric,))
+    if mode not in ("fast", "exact"):
+        raise ValueError("ERROR: mode must be 'fast' or 'exact'")
+    host = _is_host(q, r)
+    qd, rd = _dev(q, torch.float64), _dev(r, torch.float64)
+    if qd.dim() != 2 or rd.dim() != 2 or qd.shape[1] != rd.shape[1]:
+        raise ValueError("ERROR: q and r must be 2-D with the same number of columns")
+    n, g = qd.shape
+    m = rd.shape[0]
+    k = int(k)
+    if k < 1 or k + (1 if drop_first else 0) > m:
+        raise ValueError("ERROR: k=%d is not in 1..%d" % (k, m - (1 if drop_first else 0)))
+    md = _mask_dev(ref_mask)
+    if md is not None and md.numel() != m:
+        raise ValueError("ERROR: ref_mask must have one entry per reference cell")
+    idx = torch.empty((n, k), dtype=torch.int32, device=qd.device)
+    dst = torch.empty((n, k), dtype=torch.float64, device=qd.device)
+    mode_i = MODE_FAST if mode == "fast" else MODE_EXACT
+    L = lib()
+    ws_bytes = int(L.nabo_knn_workspace_bytes(n, m, g, k, METRICS[metric], mode_i))
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=qd.device)
+    stats = (C.c_int64 * 4)() if return_stats else None
+    check(L.nabo_knn(_ptr(qd), g, _ptr(rd), g, n, m, g, k, METRICS[metric], float(dist_factor), _ptr(md),
+                     1 if drop_first else 0, int(idx_offset), mode_i, _ptr(idx), _ptr(dst), _ptr(ws),
+                     ws.numel(), stats, C.c_void_p(_stream())), "knn")
+    res = (_out(idx, host), _out(dst, host))
+    if return_stats:
+        res = res + ({"rows_reranked": int(stats[0]), "rows_exact_fallback": int(stats[1]),
+                      "candidates_per_row": int(stats[2])},)
+    return res
+
+
+def rerank_exact(q, r, cand, k: int, metric: str = "euclidean", dist_factor: float = 0.25, ref_mask=None,
+                 drop_first: bool = False, idx_offset: int = 0):
+    """Exact FP64 re-rank (reference arithmetic order) of caller-supplied candidates."""
+    require_device()
+    host = _is_host(q, r, cand)
+    qd, rd = _dev(q, torch.float64), _dev(r, torch.float64)
+    cd = _dev(cand, torch.int32)
+    n, g = qd.shape
+    m = rd.shape[0]
+    md = _mask_dev(ref_mask)
+    idx = torch.empty((n, k), dtype=torch.int32, device=qd.device)
+    dst = torch.empty((n, k), dtype=torch.float64, device=qd.device)
+    check(lib().nabo_rerank_exact(_ptr(qd), g, _ptr(rd), g, n, m, g, int(k), METRICS[metric], float(dist_factor),
+                                  _ptr(md), 1 if drop_first else 0, int(idx_offset), _ptr(cd), cd.shape[1],
+                                  _ptr(idx), _ptr(dst), C.c_void_p(_stream())), "rerank_exact")
+    return _out(idx, host), _out(dst, host)
+
+
+def merge_topk(idx, dist, k: Optional[int] = None):
+    """Merge shard-major candidates (S,N,k) by (dist, idx): the reference-sharded result."""
+    require_device()
+    host = _is_host(idx, dist)
+    i_d, d_d = _dev(idx, torch.int32), _dev(dist, torch.float64)
+    if i_d.dim() != 3 or i_d.shape != d_d.shape:
+        raise ValueError("ERROR: idx and dist must both be (n_shards, n_query, k)")
+    s, n, kk = i_d.shape
+    if k is not None and k != kk:
+        raise ValueError("ERROR: k must equal the per-shard k")
+    oi = torch.empty((n, kk), dtype=torch.int32, device=i_d.device)
+    od = torch.empty((n, kk), dtype=torch.float64, device=i_d.device)
+    check(lib().nabo_merge_topk(_ptr(i_d), _ptr(d_d), s, n, kk, _ptr(oi), _ptr(od), C.c_void_p(_stream())),
+          "merge_topk")
+    return _out(oi, host), _out(od, host)
+
+
+# ----------------------------------------------------------------------------- (4) SNN weights
+def snn_weight_lut(k: int) -> np.ndarray:
+    """weight(snn) = round(snn / (2*(k-1) - snn), 2) with Python's round() on a double
+    (nabo/_mapping.py:185, 194).  Entry 0 = 0.0 (no edge, :195).  k=2 raises
+    ZeroDivisionError for snn=2 exactly as the reference does."""
+    factor = 2 * (k - 1)
+    lut = np.zeros(k + 1, dtype=np.float64)
+    for snn in range(1, k + 1):
+        lut[snn] = round(snn / (factor - snn), 2)
+    return lut
+
+
+def fix_weight(k: int) -> float:
+    """Default weight of repair edges (nabo/_mapping.py:478-479)."""
+    return 0.5 / ((2 * (k - 1)) - 0.5)
+
+
+def snn_weights(tgt_knn, ref_knn, k: Optional[int] = None):
+    """``_calc_snn`` (nabo/_mapping.py:151-200) in array form.
+    Returns (counts uint8 (N,k), weights float64 (N,k)); an edge exists where counts > 0."""
+    require_device()
+    host = _is_host(tgt_knn, ref_knn)
+    td, rd = _dev(tgt_knn, torch.int32), _dev(ref_knn, torch.int32)
+    n, kk = td.shape
+    if k is None:
+        k = kk
+    if k != kk:
+        td = td[:, :k].contiguous()
+    lut = _dev(snn_weight_lut(k), torch.float64)
+    cnt = torch.empty((n, k), dtype=torch.uint8, device=td.device)
+    w = torch.empty((n, k), dtype=torch.float64, device=td.device)
+    check(lib().nabo_snn_weights(_ptr(td), n, k, _ptr(rd), rd.shape[0], rd.shape[1], _ptr(lut), _ptr(cnt),
+                                 _ptr(w), C.c_void_p(_stream())), "snn_weights")
+    return _out(cnt, host), _out(w, host)
+
+
+# ----------------------------------------------------------------------------- (5) scores
+def mapping_scores(tgt_knn, counts, n_ref: int, k: Optional[int] = None, include=None, min_weight: float = 0.0,
+                   min_score: float = 0.0, weighted: bool = True, score_multiplier: float = 1000.0):
+    """Core of ``Graph.get_mapping_score`` (nabo/_graph.py:643-653, 690-693) in array form."""
+    require_device()
+    host = _is_host(tgt_knn, counts)
+    td, cd = _dev(tgt_knn, torch.int32), _dev(counts, torch.uint8)
+    n, kk = td.shape
+    k = kk if k is None else k
+    lut = _dev(snn_weight_lut(k), torch.float64)
+    inc = None
+    n_inc = n
+    if include is not None:
+        inc_h = np.asarray(include.cpu() if isinstance(include, torch.Tensor) else include)
+        if inc_h.dtype != np.bool_ and inc_h.dtype != np.uint8:
+            b = np.zeros(n, dtype=np.uint8)
+            b[inc_h] = 1
+            inc_h = b
+        inc_h = inc_h.astype(np.uint8)
+        n_inc = int(inc_h.sum())
+        inc = _dev(inc_h, torch.uint8)
+    out = torch.empty(n_ref, dtype=torch.float64, device=td.device)
+    L = lib()
+    ws_bytes = int(L.nabo_scores_workspace_bytes(n, kk, n_ref))
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=td.device)
+    check(L.nabo_mapping_scores(_ptr(td), _ptr(cd), _ptr(lut), n, kk, int(n_ref), _ptr(inc), n_inc,
+                                float(min_weight), 1 if weighted else 0, float(score_multiplier),
+                                float(min_score), _ptr(out), _ptr(ws), ws.numel(), C.c_void_p(_stream())),
+          "mapping_scores")
+    return _out(out, host)
+
+
+def classify_targets(tgt_knn, counts, ref_labels, n_labels: int, k: Optional[int] = None,
+                     weight_frac: float = 0.5, min_degree: int = 2, min_weight: float = 0.1):
+    """Array form of ``Graph.classify_target`` (nabo/_graph.py:722-792); -1 = na_label."""
+    require_device()
+    host = _is_host(tgt_knn, counts, ref_labels)
+    td, cd, ld = _dev(tgt_knn, torch.int32), _dev(counts, torch.uint8), _dev(ref_labels, torch.int32)
+    n, kk = td.shape
+    lut = _dev(snn_weight_lut(kk if k is None else k), torch.float64)
+    out = torch.empty(n, dtype=torch.int32, device=td.device)
+    check(lib().nabo_classify_targets(_ptr(td), _ptr(cd), _ptr(lut), n, kk, _ptr(ld), int(n_labels),
+                                      float(weight_frac), int(min_degree), float(min_weight), _ptr(out),
+                                      C.c_void_p(_stream())), "classify_targets")
+    return _out(out, host)
+
+
+# ----------------------------------------------------------------------------- (6) projection
+def project(counts, gene_idx, sf, mu, sigma, components, mean):
+    """``get_scaled_values`` + ``transform_pca`` (nabo/_dataset.py:905-913, 1028) on a dense
+    (cells x genes) count block.  ``gene_idx`` = column of each model gene (-1 = missing)."""
+    require_device()
+    host = _is_host(counts)
+    cd = _dev(counts, torch.float32)
+    gi = _dev(gene_idx, torch.int32)
+    sfd = _dev(sf, torch.float32)
+    mud, sgd = _dev(mu, torch.float64), _dev(sigma, torch.float64)
+    cm, mn = _dev(components, torch.float64), _dev(mean, torch.float64)
+    n, ld = cd.shape
+    nc, G = cm.shape
+    if not (gi.numel() == G == mud.numel() == sgd.numel() == mn.numel()):
+        raise ValueError("ERROR: gene_idx, mu, sigma, mean and components disagree on the number of genes")
+    if sfd.numel() != n:
+        raise ValueError("ERROR: one size factor per cell is required")
+    out = torch.empty((n, nc), dtype=torch.float64, device=cd.device)
+    check(lib().nabo_project_dense(_ptr(cd), ld, n, _ptr(gi), G, _ptr(sfd), _ptr(mud), _ptr(sgd), _ptr(cm),
+                                   _ptr(mn), nc, _ptr(out), nc, C.c_void_p(_stream())), "project_dense")
+    return _out(out, host)
+
+
+def project_csr(indptr, col, val, gene_pos, sf, mu, sigma, components, mean):
+    """Same projection from CSR counts over all genes of the dataset (the layout of the
+    reference's ``cell_data`` group, nabo/_io.py:103).  ``gene_pos[j]`` = position of dataset
+    gene j in the model's gene order, or -1."""
+    require_device()
+    host = _is_host(indptr, col, val)
+    ip, cl, vl = _dev(indptr, torch.int64), _dev(col, torch.int32), _dev(val, torch.float32)
+    gp = _dev(gene_pos, torch.int32)
+    sfd = _dev(sf, torch.float32)
+    mud, sgd = _dev(mu, torch.float64), _dev(sigma, torch.float64)
+    cm, mn = _dev(components, torch.float64), _dev(mean, torch.float64)
+    n = ip.numel() - 1
+    nc, G = cm.shape
+    out = torch.empty((n, nc), dtype=torch.float64, device=ip.device)
+    L = lib()
+    ws = torch.empty(int(L.nabo_project_csr_workspace_bytes(G, nc)), dtype=torch.uint8, device=ip.device)
+    check(L.nabo_project_csr(_ptr(ip), _ptr(cl), _ptr(vl), n, _ptr(gp), gp.numel(), G, _ptr(sfd), _ptr(mud),
+                             _ptr(sgd), _ptr(cm), _ptr(mn), nc, _ptr(out), nc, _ptr(ws), ws.numel(),
+                             C.c_void_p(_stream())), "project_csr")
+    return _out(out, host)
+
+
+# ----------------------------------------------------------------------------- whole path
+def map_cells(target, ref, ref_knn, k: int, metric: Optional[str] = None, dist_factor: float = 0.25,
+              ref_mask=None, mode: str = "fast", pca_model: Optional[Dict] = None,
+              scores: bool = True) -> Dict[str, object]:
+    """The hot path end to end for one target sample (what ``Dataset.transform_pca`` ->
+    ``Mapping.map_target`` -> ``Graph.get_mapping_score`` compute, minus the files):
+
+      target   (N,g) float64 PCA coordinates, or raw counts (N,genes) when ``pca_model`` is
+               given as dict(gene_idx, sf, mu, sigma, components, mean)
+      ref      (M,g) float64 reference PCA coordinates
+      ref_knn  (M,k) int32 reference self-kNN (``make_ref_graph``'s sorted rows)
+
+    Returns dict(idx, dist, counts, weights, scores[, pca]) - NumPy if the inputs were."""
+    host = _is_host(target, ref, ref_knn)
+    res: Dict[str, object] = {}
+    if pca_model is not None:
+        tq = project(_dev(target, torch.float32), pca_model["gene_idx"], pca_model["sf"], pca_model["mu"],
+                     pca_model["sigma"], pca_model["components"], pca_model["mean"])
+        g = _dev(ref, torch.float64).shape[1]
+        res["pca"] = tq
+        tq = tq[:, :g].contiguous()
+    else:
+        tq = _dev(target, torch.float64)
+    rd = _dev(ref, torch.float64)
+    rk = _dev(ref_knn, torch.int32)
+    m = resolve_metric(metric, False)
+    idx, dst = knn(tq, rd, k, m, dist_factor, ref_mask, False, 0, mode)
+    cnt, w = snn_weights(idx, rk, k)
+    res.update(idx=idx, dist=dst, counts=cnt, weights=w)
+    if scores:
+        res["scores"] = mapping_scores(idx, cnt, rd.shape[0], k)
+    if host:
+        res = {k_: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k_, v in res.items()}
+    return res

@@ -1,0 +1,514 @@
+// Exact FP64 kernels in the reference's arithmetic order.
+//   * full distance tiles  (replace _euclidean_dist / _mod_canberra_dist, nabo/_mapping.py:16-45)
+//   * brute-force distance + fused per-query top-k  (replace _calc_dist, :48-148)
+//   * exact re-rank of nominated candidates
+// All accumulate over dimensions k = 0..g-1 sequentially with separate multiply and
+// add (__dmul_rn/__dadd_rn forbid FMA contraction), so results are bit-identical to the
+// numba loops.  The brute-force kernel never writes the N x M matrix: each 64x64 tile
+// is filtered against the running k-th best of its query and only survivors reach a
+// per-query shared-memory buffer that a warp compacts with a bitonic sort.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------ error channel
+static thread_local char g_err[512] = "";
+int nabo_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+extern "C" const char* nabo_last_error(void) { return g_err; }
+extern "C" int nabo_abi_version(void) { return NABO_ABI_VERSION; }
+extern "C" int nabo_device_check(int* sm_count) {
+    int dev = 0;
+    NABO_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    NABO_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (p.major != 10)
+        return nabo_set_error(NABO_EUNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only",
+                              p.name, p.major, p.minor);
+    return 0;
+}
+
+// ------------------------------------------------------------------ per-pair arithmetic
+template <int METRIC>
+struct Pair {
+    // one dimension
+    static __device__ __forceinline__ double step(double acc, double x, double y, double f) {
+        if (METRIC == NABO_EUCLIDEAN) {
+            double t = __dsub_rn(x, y);
+            return __dadd_rn(acc, __dmul_rn(t, t));
+        } else if (METRIC == NABO_MOD_CANBERRA) {
+            double absx = fabs(x);
+            double num = fabs(__dsub_rn(x, y));
+            if (num < __dmul_rn(f, absx)) {
+                double den = __dadd_rn(__dadd_rn(absx, fabs(y)), 0.01);
+                return __dadd_rn(acc, __ddiv_rn(num, den));
+            }
+            return __dadd_rn(acc, 1.0);
+        } else {
+            return __dadd_rn(acc, __dmul_rn(x, y));
+        }
+    }
+    // nq, nr: squared norms (cosine only)
+    static __device__ __forceinline__ double finish(double acc, double nq, double nr) {
+        if (METRIC == NABO_EUCLIDEAN) return __dsqrt_rn(acc);
+        if (METRIC == NABO_MOD_CANBERRA) return acc;
+        return __dsub_rn(1.0, __ddiv_rn(acc, __dmul_rn(__dsqrt_rn(nq), __dsqrt_rn(nr))));
+    }
+};
+
+__device__ __forceinline__ double seq_sqnorm(const double* v, int g) {
+    double s = 0.0;
+    for (int k = 0; k < g; ++k) s = __dadd_rn(s, __dmul_rn(v[k], v[k]));
+    return s;
+}
+
+// ------------------------------------------------------------------ tile geometry
+constexpr int TQ = 64;          // queries per block
+constexpr int TR = 64;          // references per step
+constexpr int NT = 256;         // threads: 16 x 16, each owns a 4 x 4 micro tile
+constexpr int LDS_T = TQ + 2;   // padded row stride of the k-major tiles (keeps 16 B alignment)
+
+__device__ __forceinline__ void load_tile_kmajor(double* s, const double* __restrict__ src, int ld,
+                                                 int row0, int nrows, int g, const int* row_ids) {
+    // s[k * LDS_T + r] = src[row(row0 + r)][k]; rows past nrows are zero-filled
+    for (int e = threadIdx.x; e < TQ * g; e += NT) {
+        int r = e / g, k = e - r * g;
+        int row = row0 + r;
+        double v = 0.0;
+        if (row < nrows) {
+            long long rr = row_ids ? row_ids[row] : row;
+            v = src[rr * (long long)ld + k];
+        }
+        s[k * LDS_T + r] = v;
+    }
+}
+
+// ------------------------------------------------------------------ (1) distance tiles
+template <int METRIC>
+__global__ void __launch_bounds__(NT) dist_tile_kernel(const double* __restrict__ x, int ldx,
+                                                       const double* __restrict__ y, int ldy,
+                                                       double* __restrict__ d, int ldd, int m, int n,
+                                                       int g, double f) {
+    extern __shared__ double smem[];
+    double* xs = smem;
+    double* ys = smem + (size_t)g * LDS_T;
+    __shared__ double nqs[TQ], nrs[TR];
+    const int q0 = blockIdx.y * TQ, r0 = blockIdx.x * TR;
+    load_tile_kmajor(xs, x, ldx, q0, m, g, nullptr);
+    load_tile_kmajor(ys, y, ldy, r0, n, g, nullptr);
+    __syncthreads();
+    if (METRIC == NABO_COSINE) {
+        if (threadIdx.x < TQ) {
+            double s = 0.0;
+            for (int k = 0; k < g; ++k) { double v = xs[k * LDS_T + threadIdx.x]; s = __dadd_rn(s, __dmul_rn(v, v)); }
+            nqs[threadIdx.x] = s;
+        } else if (threadIdx.x < TQ + TR) {
+            int t = threadIdx.x - TQ;
+            double s = 0.0;
+            for (int k = 0; k < g; ++k) { double v = ys[k * LDS_T + t]; s = __dadd_rn(s, __dmul_rn(v, v)); }
+            nrs[t] = s;
+        }
+        __syncthreads();
+    }
+    const int tr = threadIdx.x & 15, tq = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int k = 0; k < g; ++k) {
+        double xv[4], yv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) xv[a] = xs[k * LDS_T + tq * 4 + a];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) yv[b] = ys[k * LDS_T + tr * 4 + b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = Pair<METRIC>::step(acc[a][b], xv[a], yv[b], f);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        int qi = q0 + tq * 4 + a;
+        if (qi >= m) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int rj = r0 + tr * 4 + b;
+            if (rj < n) {
+                double nq = METRIC == NABO_COSINE ? nqs[tq * 4 + a] : 0.0;
+                double nr = METRIC == NABO_COSINE ? nrs[tr * 4 + b] : 0.0;
+                d[(long long)qi * ldd + rj] = Pair<METRIC>::finish(acc[a][b], nq, nr);
+            }
+        }
+    }
+}
+
+template <int METRIC>
+static int launch_dist_tiles(const double* x, int ldx, const double* y, int ldy, double* d, int ldd,
+                             int m, int n, int g, double f, cudaStream_t s) {
+    NABO_ARG(m >= 0 && n >= 0 && g >= 1, "dist: bad shape m=%d n=%d g=%d", m, n, g);
+    NABO_ARG(ldx >= g && ldy >= g && ldd >= n, "dist: leading dimension smaller than row length");
+    if (m == 0 || n == 0) return 0;
+    NABO_ARG(x && y && d, "dist: null pointer");
+    size_t smem = 2 * (size_t)g * LDS_T * sizeof(double);
+    NABO_ARG(smem <= 200 * 1024, "dist: g=%d exceeds the shared-memory tile (max %d dims)", g,
+             (int)(200 * 1024 / (2 * LDS_T * sizeof(double))));
+    NABO_CUDA(cudaFuncSetAttribute(dist_tile_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((n + TR - 1) / TR, (m + TQ - 1) / TQ);
+    dist_tile_kernel<METRIC><<<grid, NT, smem, s>>>(x, ldx, y, ldy, d, ldd, m, n, g, f);
+    NABO_LAUNCH_CHECK("dist_tile_kernel");
+    return 0;
+}
+
+extern "C" int nabo_euclidean_dist(const double* x, int ldx, const double* y, int ldy, double* d, int ldd,
+                                   int m, int n, int g, void* stream) {
+    return launch_dist_tiles<NABO_EUCLIDEAN>(x, ldx, y, ldy, d, ldd, m, n, g, 0.0, (cudaStream_t)stream);
+}
+extern "C" int nabo_mod_canberra_dist(const double* x, int ldx, const double* y, int ldy, double* d, int ldd,
+                                      int m, int n, int g, double f, void* stream) {
+    return launch_dist_tiles<NABO_MOD_CANBERRA>(x, ldx, y, ldy, d, ldd, m, n, g, f, (cudaStream_t)stream);
+}
+extern "C" int nabo_cosine_dist(const double* x, int ldx, const double* y, int ldy, double* d, int ldd,
+                                int m, int n, int g, void* stream) {
+    return launch_dist_tiles<NABO_COSINE>(x, ldx, y, ldy, d, ldd, m, n, g, 0.0, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ (2) brute force + fused top-k
+// Per-query candidate buffer of CAP (d, i) pairs in shared memory.  A tile appends at
+// most TR entries per query, so compacting whenever count > CAP - TR keeps it in bounds.
+struct ExactSmem {
+    double* xs;     // [g][LDS_T]
+    double* ys;     // [g][LDS_T]
+    double* bd;     // [TQ][CAP]
+    int* bi;        // [TQ][CAP]
+    double* tau_d;  // [TQ]
+    double* nq;     // [TQ]
+    double* nr;     // [TR]
+    int* tau_i;     // [TQ]
+    int* cnt;       // [TQ]
+};
+
+__device__ __forceinline__ ExactSmem carve_exact(double* base, int g, int cap) {
+    ExactSmem s;
+    s.xs = base;
+    s.ys = s.xs + (size_t)g * LDS_T;
+    s.bd = s.ys + (size_t)g * LDS_T;
+    s.tau_d = s.bd + (size_t)TQ * cap;
+    s.nq = s.tau_d + TQ;
+    s.nr = s.nq + TQ;
+    s.bi = (int*)(s.nr + TR);
+    s.tau_i = s.bi + (size_t)TQ * cap;
+    s.cnt = s.tau_i + TQ;
+    return s;
+}
+static size_t exact_smem_bytes(int g, int cap) {
+    return (2 * (size_t)g * LDS_T + (size_t)TQ * cap + 3 * TQ) * sizeof(double) +
+           ((size_t)TQ * cap + 2 * TQ) * sizeof(int);
+}
+
+// one warp: sort the buffer of query q, keep the best ksel, refresh tau
+__device__ __forceinline__ void compact_query(const ExactSmem& s, int q, int cap, int ksel, int lane) {
+    double* d = s.bd + (size_t)q * cap;
+    int* ix = s.bi + (size_t)q * cap;
+    int n = s.cnt[q];
+    for (int t = n + lane; t < cap; t += 32) { d[t] = CUDART_INF; ix[t] = 0x7fffffff; }
+    __syncwarp();
+    warp_bitonic_sort(d, ix, cap, lane);
+    if (lane == 0) {
+        if (n >= ksel) {
+            s.cnt[q] = ksel;
+            s.tau_d[q] = d[ksel - 1];
+            s.tau_i[q] = ix[ksel - 1];
+        }
+    }
+    __syncwarp();
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(NT, 1)
+knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ r, int ldr, int n_query,
+                 int n_ref, int g, int k, double f, const uint8_t* __restrict__ mask, int drop_first,
+                 int idx_offset, const int* __restrict__ row_ids, const int* __restrict__ n_rows_dev,
+                 int cap, int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    extern __shared__ double smem[];
+    const ExactSmem s = carve_exact(smem, g, cap);
+    const int nq_total = n_rows_dev ? *n_rows_dev : n_query;   // fallback mode: row list on device
+    const int q0 = blockIdx.x * TQ;
+    if (q0 >= nq_total) return;
+    const int ksel = k + (drop_first ? 1 : 0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tr = threadIdx.x & 15, tq = threadIdx.x >> 4;
+
+    load_tile_kmajor(s.xs, q, ldq, q0, nq_total, g, row_ids);
+    if (threadIdx.x < TQ) {
+        s.cnt[threadIdx.x] = 0;
+        s.tau_d[threadIdx.x] = CUDART_INF;
+        s.tau_i[threadIdx.x] = 0x7fffffff;
+    }
+    __syncthreads();
+    if (METRIC == NABO_COSINE && threadIdx.x < TQ) {
+        double acc = 0.0;
+        for (int kk = 0; kk < g; ++kk) { double v = s.xs[kk * LDS_T + threadIdx.x]; acc = __dadd_rn(acc, __dmul_rn(v, v)); }
+        s.nq[threadIdx.x] = acc;
+    }
+
+    for (int r0 = 0; r0 < n_ref; r0 += TR) {
+        __syncthreads();   // previous tile fully consumed (and compaction finished)
+        load_tile_kmajor(s.ys, r, ldr, r0, n_ref, g, nullptr);
+        __syncthreads();
+        if (METRIC == NABO_COSINE) {
+            if (threadIdx.x < TR) {
+                double acc = 0.0;
+                for (int kk = 0; kk < g; ++kk) { double v = s.ys[kk * LDS_T + threadIdx.x]; acc = __dadd_rn(acc, __dmul_rn(v, v)); }
+                s.nr[threadIdx.x] = acc;
+            }
+            __syncthreads();
+        }
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int kk = 0; kk < g; ++kk) {
+            double xv[4], yv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) xv[a] = s.xs[kk * LDS_T + tq * 4 + a];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) yv[b] = s.ys[kk * LDS_T + tr * 4 + b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = Pair<METRIC>::step(acc[a][b], xv[a], yv[b], f);
+        }
+        // filter against the running k-th best and append survivors
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int ql = tq * 4 + a;
+            if (q0 + ql >= nq_total) continue;
+            const double td = s.tau_d[ql];
+            const int ti = s.tau_i[ql];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = r0 + tr * 4 + b;
+                if (j >= n_ref) continue;
+                double d = Pair<METRIC>::finish(acc[a][b], METRIC == NABO_COSINE ? s.nq[ql] : 0.0,
+                                                METRIC == NABO_COSINE ? s.nr[tr * 4 + b] : 0.0);
+                if (d != d || (mask && mask[j])) d = CUDART_INF;   // NaN / ignored -> last
+                if (nabo_less(d, j, td, ti)) {
+                    int pos = atomicAdd(&s.cnt[ql], 1);
+                    s.bd[(size_t)ql * cap + pos] = d;
+                    s.bi[(size_t)ql * cap + pos] = j;
+                }
+            }
+        }
+        __syncthreads();
+        for (int ql = warp; ql < TQ; ql += NT / 32)
+            if (s.cnt[ql] > cap - TR) compact_query(s, ql, cap, ksel, lane);
+    }
+    __syncthreads();
+    // final sort + write-out
+    for (int ql = warp; ql < TQ; ql += NT / 32) {
+        const int qi = q0 + ql;
+        if (qi >= nq_total) continue;
+        const int n_have = s.cnt[ql];
+        {
+            double* d = s.bd + (size_t)ql * cap;
+            int* ix = s.bi + (size_t)ql * cap;
+            for (int t = n_have + lane; t < cap; t += 32) { d[t] = CUDART_INF; ix[t] = 0x7fffffff; }
+            __syncwarp();
+            warp_bitonic_sort(d, ix, cap, lane);
+        }
+        const long long orow = row_ids ? row_ids[qi] : qi;
+        const int skip = drop_first ? 1 : 0;
+        for (int t = lane; t < k; t += 32) {
+            int src = t + skip;
+            int id = -1;
+            double dv = CUDART_NAN;
+            if (src < n_have && src < cap) {
+                id = s.bi[(size_t)ql * cap + src];
+                dv = s.bd[(size_t)ql * cap + src];
+                if (mask && mask[id]) dv = CUDART_NAN;
+                else if (dv == CUDART_INF) {
+                    // NaN distances were keyed as +inf: recompute to tell them from a true inf
+                    dv = CUDART_NAN;
+                }
+                id += idx_offset;
+            }
+            out_idx[orow * k + t] = id;
+            out_dist[orow * k + t] = dv;
+        }
+    }
+}
+
+static int exact_cap_for(int ksel) {
+    int kp = nabo_next_pow2(ksel);
+    int cap = 2 * kp;
+    if (cap < 128) cap = 128;
+    return cap;
+}
+
+int nabo_knn_exact_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
+                          int k, int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
+                          const int* row_ids, const int* n_rows_dev, int32_t* out_idx, double* out_dist,
+                          cudaStream_t st) {
+    const int ksel = k + (drop_first ? 1 : 0);
+    NABO_ARG(k >= 1 && ksel <= 128, "knn: k=%d unsupported (1 <= k, k + drop_first <= 128)", k);
+    NABO_ARG(g >= 1, "knn: g=%d", g);
+    if (n_query == 0) return 0;
+    const int cap = exact_cap_for(ksel);
+    size_t smem = exact_smem_bytes(g, cap);
+    NABO_ARG(smem <= 227 * 1024, "knn: g=%d with k=%d needs %zu B of shared memory (max 232448)", g, k, smem);
+    dim3 grid((n_query + TQ - 1) / TQ);
+#define LAUNCH(M)                                                                                         \
+    NABO_CUDA(cudaFuncSetAttribute(knn_exact_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    knn_exact_kernel<M><<<grid, NT, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, \
+                                                idx_offset, row_ids, n_rows_dev, cap, out_idx, out_dist);
+    if (metric == NABO_EUCLIDEAN) { LAUNCH(NABO_EUCLIDEAN) }
+    else if (metric == NABO_MOD_CANBERRA) { LAUNCH(NABO_MOD_CANBERRA) }
+    else if (metric == NABO_COSINE) { LAUNCH(NABO_COSINE) }
+    else return nabo_set_error(NABO_EINVAL, "knn: unknown metric %d", metric);
+#undef LAUNCH
+    NABO_LAUNCH_CHECK("knn_exact_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------ exact re-rank of candidates
+// One warp per query.  cand (n_query x n_cand) holds LOCAL reference indices, -1 = empty.
+// If cert_tau != nullptr the kernel also evaluates the candidate certificate: the k-th
+// exact score must lie strictly below cert_tau[q] - cert_eps[q] (both in the SCORE space of
+// the candidate pass: squared distance for Euclidean, distance otherwise); rows that fail
+// are appended to fail_rows (count in fail_count) for the exact fallback.
+template <int METRIC>
+__global__ void __launch_bounds__(128)
+rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ r, int ldr, int n_query,
+              int n_ref, int g, int k, double f, const uint8_t* __restrict__ mask, int drop_first,
+              int idx_offset, const int32_t* __restrict__ cand, int n_cand, int capp,
+              const float* __restrict__ cert_tau, const float* __restrict__ cert_eps,
+              int* __restrict__ fail_rows, int* __restrict__ fail_count,
+              int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = blockIdx.x * 4 + warp;
+    if (qi >= n_query) return;
+    double* d = smem + (size_t)warp * capp * 2;           // keys (final distance)
+    double* sc = d + capp;                                  // scores (pre-sqrt for Euclidean)
+    int* ix = (int*)(smem + (size_t)4 * capp * 2) + (size_t)warp * capp;
+    const double* x = q + (long long)qi * ldq;
+    double nq = 0.0;
+    if (METRIC == NABO_COSINE) nq = seq_sqnorm(x, g);
+    int n_valid = 0;
+    for (int c = lane; c < capp; c += 32) {
+        int j = c < n_cand ? cand[(long long)qi * n_cand + c] : -1;
+        double key = CUDART_INF, score = CUDART_INF;
+        int id = 0x7fffffff;
+        if (j >= 0 && j < n_ref) {
+            const double* y = r + (long long)j * ldr;
+            double acc = 0.0;
+            for (int kk = 0; kk < g; ++kk) acc = Pair<METRIC>::step(acc, x[kk], y[kk], f);
+            double nr = 0.0;
+            if (METRIC == NABO_COSINE) nr = seq_sqnorm(y, g);
+            double dv = Pair<METRIC>::finish(acc, nq, nr);
+            score = METRIC == NABO_EUCLIDEAN ? acc : dv;
+            if (dv != dv || (mask && mask[j])) { dv = CUDART_INF; score = CUDART_INF; }
+            key = dv;
+            id = j;
+        }
+        d[c] = key; sc[c] = score; ix[c] = id;
+        n_valid += (id != 0x7fffffff);
+    }
+    __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+    // sort by (key, idx); scores follow their keys (monotone map, so recompute from position is
+    // unnecessary: carry them through a second pass keyed by idx lookup)
+    // -> simple approach: sort (key, idx), then fetch score of the k-th entry by searching ix.
+    // Keep a copy of unsorted (idx, score) in registers of the owning lanes.
+    int my_id[4];
+    double my_sc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        int c = lane + 32 * u;
+        my_id[u] = c < capp ? ix[c] : 0x7fffffff;
+        my_sc[u] = c < capp ? sc[c] : CUDART_INF;
+    }
+    __syncwarp();
+    warp_bitonic_sort(d, ix, capp, lane);
+    const int skip = drop_first ? 1 : 0;
+    const int ksel = k + skip;
+    for (int t = lane; t < k; t += 32) {
+        int src = t + skip;
+        int id = -1;
+        double dv = CUDART_NAN;
+        if (src < n_valid) {
+            id = ix[src];
+            dv = d[src];
+            if (dv == CUDART_INF) dv = CUDART_NAN;
+            id += idx_offset;
+        }
+        out_idx[(long long)qi * k + t] = id;
+        out_dist[(long long)qi * k + t] = dv;
+    }
+    if (cert_tau) {
+        // score of the ksel-th best candidate
+        bool fail;
+        if (n_valid < ksel) {
+            // fewer candidates than needed: only acceptable when nothing was rejected
+            fail = !(cert_tau[qi] == CUDART_INF_F);
+        } else {
+            int kid = ix[ksel - 1];
+            double ks = CUDART_INF;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (my_id[u] == kid) ks = my_sc[u];
+            for (int o = 16; o > 0; o >>= 1) ks = fmin(ks, __shfl_xor_sync(0xffffffffu, ks, o));
+            double bound = (double)cert_tau[qi] - (double)cert_eps[qi];
+            fail = !(ks < bound);
+            if (cert_tau[qi] == CUDART_INF_F) fail = false;   // nothing was rejected
+        }
+        if (fail && lane == 0) {
+            int p = atomicAdd(fail_count, 1);
+            fail_rows[p] = qi;
+        }
+    }
+}
+
+int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
+                       int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
+                       const int32_t* cand, int n_cand, const float* cert_tau, const float* cert_eps,
+                       int* fail_rows, int* fail_count, int32_t* out_idx, double* out_dist, cudaStream_t st) {
+    NABO_ARG(n_cand >= 1 && n_cand <= 128, "rerank: n_cand=%d unsupported (1..128)", n_cand);
+    NABO_ARG(k >= 1 && k + (drop_first ? 1 : 0) <= n_cand, "rerank: k=%d does not fit n_cand=%d", k, n_cand);
+    if (n_query == 0) return 0;
+    int capp = nabo_next_pow2(n_cand);
+    if (capp < 32) capp = 32;
+    size_t smem = (size_t)4 * capp * (2 * sizeof(double) + sizeof(int));
+    dim3 grid((n_query + 3) / 4);
+#define LAUNCH(M)                                                                                              \
+    rerank_kernel<M><<<grid, 128, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first,       \
+                                              idx_offset, cand, n_cand, capp, cert_tau, cert_eps, fail_rows,   \
+                                              fail_count, out_idx, out_dist);
+    if (metric == NABO_EUCLIDEAN) { LAUNCH(NABO_EUCLIDEAN) }
+    else if (metric == NABO_MOD_CANBERRA) { LAUNCH(NABO_MOD_CANBERRA) }
+    else if (metric == NABO_COSINE) { LAUNCH(NABO_COSINE) }
+    else return nabo_set_error(NABO_EINVAL, "rerank: unknown metric %d", metric);
+#undef LAUNCH
+    NABO_LAUNCH_CHECK("rerank_kernel");
+    return 0;
+}
+
+extern "C" int nabo_rerank_exact(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref,
+                                 int g, int k, int metric, double dist_factor, const uint8_t* ref_mask,
+                                 int drop_first, int idx_offset, const int32_t* cand, int n_cand,
+                                 int32_t* out_idx, double* out_dist, void* stream) {
+    NABO_ARG(q && r && cand && out_idx && out_dist, "rerank: null pointer");
+    NABO_ARG(ldq >= g && ldr >= g, "rerank: leading dimension smaller than g");
+    return nabo_rerank_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, dist_factor, ref_mask, drop_first,
+                              idx_offset, cand, n_cand, nullptr, nullptr, nullptr, nullptr, out_idx, out_dist,
+                              (cudaStream_t)stream);
+}

@@ -1,0 +1,338 @@
+// SNN neighbour weights, per-reference mapping scores, target classification and the
+// shard merge.  Integer / gather work bounded by HBM, not by any FP pipe.
+//   nabo_snn_weights      <- _calc_snn                      nabo/_mapping.py:151-200
+//   nabo_mapping_scores   <- Graph.get_mapping_score core   nabo/_graph.py:643-653, 690-693
+//   nabo_classify_targets <- Graph.classify_target          nabo/_graph.py:722-792
+//   nabo_merge_topk       (reference-sharded mode; result must equal the unsharded top-k)
+#include "common.cuh"
+
+// ------------------------------------------------------------------ SNN counts + weights
+// One warp per query.  A = the query's k neighbours (shared memory); for neighbour j the
+// lanes stride over row ref_knn[j][:k_use] and test membership in A.
+__global__ void __launch_bounds__(256)
+snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, const int32_t* __restrict__ ref_knn,
+           int n_ref, int k_ref, int k_use, const double* __restrict__ lut, uint8_t* __restrict__ counts,
+           double* __restrict__ weights) {
+    extern __shared__ int sm_a[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * 8 + warp;
+    if (t >= n_query) return;
+    int* a = sm_a + warp * k;
+    for (int i = lane; i < k; i += 32) a[i] = tgt_knn[(long long)t * k + i];
+    __syncwarp();
+    for (int jj = 0; jj < k; ++jj) {
+        const int j = a[jj];
+        int c = 0;
+        if (j >= 0 && j < n_ref) {
+            const int32_t* row = ref_knn + (long long)j * k_ref;
+            for (int l = lane; l < k_use; l += 32) {
+                const int b = row[l];
+                bool hit = false;
+                if (b >= 0)
+                    for (int i = 0; i < k; ++i) hit |= (a[i] == b);
+                c += hit;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) {
+            if (counts) counts[(long long)t * k + jj] = (uint8_t)c;
+            if (weights) weights[(long long)t * k + jj] = lut[c];
+        }
+    }
+}
+
+extern "C" int nabo_snn_weights(const int32_t* tgt_knn, int n_query, int k, const int32_t* ref_knn, int n_ref,
+                                int k_ref, const double* lut, uint8_t* out_counts, double* out_weights,
+                                void* stream) {
+    NABO_ARG(k >= 1 && k <= 255 && k_ref >= 1, "snn: k=%d k_ref=%d unsupported (1..255)", k, k_ref);
+    NABO_ARG(n_query >= 0 && n_ref >= 1, "snn: bad sizes");
+    if (n_query == 0) return 0;
+    NABO_ARG(tgt_knn && ref_knn && (out_counts || out_weights), "snn: null pointer");
+    NABO_ARG(!out_weights || lut, "snn: weights requested without a lut");
+    int k_use = k < k_ref ? k : k_ref;   // ref_data[ref_c][:k], _mapping.py:193
+    snn_kernel<<<(n_query + 7) / 8, 256, 8 * k * sizeof(int), (cudaStream_t)stream>>>(
+        tgt_knn, n_query, k, ref_knn, n_ref, k_ref, k_use, lut, out_counts, out_weights);
+    NABO_LAUNCH_CHECK("snn_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------ stable LSD radix sort (keys u32, payload u32)
+constexpr int RS_THREADS = 256;
+constexpr int RS_ROUNDS = 8;
+constexpr int RS_BLOCK = RS_THREADS * RS_ROUNDS;   // elements per block, order = (round, thread)
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, uint32_t* __restrict__ hist, int nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * RS_BLOCK;
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        long long i = base + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];   // digit-major
+}
+
+// exclusive scan of `n` counters by one block (n up to a few million)
+__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t* __restrict__ a, long long n) {
+    __shared__ uint32_t part[1024];
+    const long long per = (n + 1023) / 1024;
+    const long long lo = (long long)threadIdx.x * per;
+    const long long hi = lo + per < n ? lo + per : n;
+    uint32_t s = 0;
+    for (long long i = lo; i < hi; ++i) s += a[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele over the 1024 partials
+    for (int o = 1; o < 1024; o <<= 1) {
+        uint32_t v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    for (long long i = lo; i < hi; ++i) {
+        uint32_t v = a[i];
+        a[i] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, int shift,
+                  const uint32_t* __restrict__ offs, int nblocks, uint32_t* __restrict__ okeys,
+                  uint32_t* __restrict__ ovals) {
+    __shared__ uint32_t running[256];           // elements of each digit placed by earlier rounds
+    __shared__ uint16_t wcnt[RS_THREADS / 32][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    running[threadIdx.x] = offs[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    const long long base = (long long)blockIdx.x * RS_BLOCK;
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        for (int w = 0; w < RS_THREADS / 32; ++w) wcnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        const long long i = base + r * RS_THREADS + threadIdx.x;
+        const bool live = i < n;
+        uint32_t key = live ? keys[i] : 0xFFFFFFFFu;
+        uint32_t val = live ? vals[i] : 0u;
+        const uint32_t digit = live ? ((key >> shift) & 255u) : 256u;   // 256 = idle lane group
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (live && rank_in_warp == 0) wcnt[warp][digit] = (uint16_t)__popc(peers);
+        __syncthreads();
+        if (live) {
+            uint32_t before = 0;
+            for (int w = 0; w < warp; ++w) before += wcnt[w][digit];
+            const uint32_t pos = running[digit] + before + rank_in_warp;
+            okeys[pos] = key;
+            ovals[pos] = val;
+        }
+        __syncthreads();
+        {
+            uint32_t tot = 0;
+            for (int w = 0; w < RS_THREADS / 32; ++w) tot += wcnt[w][threadIdx.x];
+            running[threadIdx.x] += tot;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ mapping scores
+__global__ void __launch_bounds__(256)
+score_edges_kernel(const int32_t* __restrict__ tgt_knn, const uint8_t* __restrict__ counts,
+                   const double* __restrict__ lut, long long n_edges, int k, int n_ref,
+                   const uint8_t* __restrict__ include, double min_weight, int weighted,
+                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int t = (int)(e / k);
+    const int r = tgt_knn[e];
+    const int c = counts[e];
+    bool keep = c > 0 && r >= 0 && r < n_ref && (!include || include[t]);
+    if (keep && weighted) keep = lut[c] > min_weight;      // _graph.py:647-648
+    keys[e] = keep ? (uint32_t)r : (uint32_t)n_ref;         // dropped edges sort past every reference
+    vals[e] = (uint32_t)e;
+}
+
+__global__ void __launch_bounds__(256)
+score_reduce_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long long n_edges,
+                    const uint8_t* __restrict__ counts, const double* __restrict__ lut, int n_ref,
+                    int weighted, double mult, double denom, double min_score, double* __restrict__ out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_ref) return;
+    // lower_bound(keys, r)
+    long long lo = 0, hi = n_edges;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (keys[mid] < (uint32_t)r) lo = mid + 1; else hi = mid;
+    }
+    double acc = 0.0;
+    for (long long p = lo; p < n_edges && keys[p] == (uint32_t)r; ++p) {
+        // edges arrive in target order (stable sort of a target-major list) = the
+        // reference's adjacency insertion order
+        acc = weighted ? __dadd_rn(acc, lut[counts[vals[p]]]) : __dadd_rn(acc, 1.0);
+    }
+    double v = __ddiv_rn(__dmul_rn(mult, acc), denom);       // score_multiplier * v / len(include_nodes)
+    out[r] = v >= min_score ? v : 0.0;
+}
+
+extern "C" size_t nabo_scores_workspace_bytes(int n_query, int k, int n_ref) {
+    size_t e = (size_t)n_query * (size_t)k;
+    size_t nblocks = (e + RS_BLOCK - 1) / RS_BLOCK;
+    (void)n_ref;
+    return 4 * nabo_align_up(e * sizeof(uint32_t), 256) + nabo_align_up(256 * nblocks * sizeof(uint32_t), 256) + 1024;
+}
+
+extern "C" int nabo_mapping_scores(const int32_t* tgt_knn, const uint8_t* counts, const double* lut, int n_query,
+                                   int k, int n_ref, const uint8_t* include, int n_include, double min_weight,
+                                   int weighted, double score_multiplier, double min_score, double* out_scores,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NABO_ARG(n_query >= 0 && k >= 1 && n_ref >= 1, "scores: bad sizes");
+    NABO_ARG((long long)n_query * k < (1ll << 31), "scores: more than 2^31 edges in one call; shard the targets");
+    NABO_ARG(out_scores && (n_query == 0 || (tgt_knn && counts && lut)), "scores: null pointer");
+    NABO_ARG(n_include > 0 || n_query == 0, "scores: n_include must be positive");
+    if (n_query == 0) {
+        NABO_CUDA(cudaMemsetAsync(out_scores, 0, sizeof(double) * n_ref, st));
+        return 0;
+    }
+    const long long e = (long long)n_query * k;
+    const int nblocks = (int)((e + RS_BLOCK - 1) / RS_BLOCK);
+    if (workspace_bytes < nabo_scores_workspace_bytes(n_query, k, n_ref))
+        return nabo_set_error(NABO_EWORKSPACE, "scores: workspace too small (%zu < %zu)", workspace_bytes,
+                              nabo_scores_workspace_bytes(n_query, k, n_ref));
+    NaboArena ar(workspace, workspace_bytes);
+    uint32_t* k0 = ar.take<uint32_t>(e);
+    uint32_t* v0 = ar.take<uint32_t>(e);
+    uint32_t* k1 = ar.take<uint32_t>(e);
+    uint32_t* v1 = ar.take<uint32_t>(e);
+    uint32_t* hist = ar.take<uint32_t>((size_t)256 * nblocks);
+    if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "scores: workspace too small");
+    score_edges_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(tgt_knn, counts, lut, e, k, n_ref, include,
+                                                                   min_weight, weighted, k0, v0);
+    NABO_LAUNCH_CHECK("score_edges_kernel");
+    int bits = 1;
+    while ((1ll << bits) <= n_ref) ++bits;          // keys go up to n_ref inclusive
+    for (int shift = 0; shift < bits; shift += 8) {
+        rs_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(k0, (int)e, shift, hist, nblocks);
+        rs_scan_kernel<<<1, 1024, 0, st>>>(hist, (long long)256 * nblocks);
+        rs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(k0, v0, (int)e, shift, hist, nblocks, k1, v1);
+        NABO_LAUNCH_CHECK("radix pass");
+        uint32_t* t = k0; k0 = k1; k1 = t;
+        t = v0; v0 = v1; v1 = t;
+    }
+    score_reduce_kernel<<<(n_ref + 255) / 256, 256, 0, st>>>(k0, v0, e, counts, lut, n_ref, weighted,
+                                                             score_multiplier, (double)n_include, min_score,
+                                                             out_scores);
+    NABO_LAUNCH_CHECK("score_reduce_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------ classify_target
+__global__ void __launch_bounds__(128)
+classify_kernel(const int32_t* __restrict__ tgt_knn, const uint8_t* __restrict__ counts,
+                const double* __restrict__ lut, int n_query, int k, const int32_t* __restrict__ ref_labels,
+                int n_labels, double weight_frac, int min_degree, double min_weight,
+                int32_t* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_query) return;
+    const int32_t* nb = tgt_knn + (long long)t * k;
+    const uint8_t* cn = counts + (long long)t * k;
+    int deg = 0;
+    double tot = 0.0;
+    for (int j = 0; j < k; ++j)
+        if (cn[j] > 0 && nb[j] >= 0) { ++deg; tot = __dadd_rn(tot, lut[cn[j]]); }   // every edge counts (:771)
+    int best = -1;
+    double best_w = -1.0;
+    if (deg >= min_degree) {
+        for (int j = 0; j < k; ++j) {
+            if (!(cn[j] > 0 && nb[j] >= 0)) continue;
+            const double wj = lut[cn[j]];
+            if (!(wj > min_weight)) continue;
+            const int lab = ref_labels[nb[j]];
+            if (lab < 0 || lab >= n_labels) continue;
+            bool first = true;
+            for (int i = 0; i < j; ++i)
+                if (cn[i] > 0 && nb[i] >= 0 && lut[cn[i]] > min_weight && ref_labels[nb[i]] == lab) { first = false; break; }
+            if (!first) continue;
+            double s = 0.0;
+            for (int i = j; i < k; ++i)
+                if (cn[i] > 0 && nb[i] >= 0 && lut[cn[i]] > min_weight && ref_labels[nb[i]] == lab)
+                    s = __dadd_rn(s, lut[cn[i]]);
+            if (s > best_w || (s == best_w && lab < best)) { best_w = s; best = lab; }
+        }
+        if (best < 0) {          // no voting edge: every cluster has weight 0; argmax -> label 0
+            best = n_labels > 0 ? 0 : -1;
+            best_w = 0.0;
+        }
+        if (!(best_w > __dmul_rn(weight_frac, tot))) best = -1;
+    }
+    out[t] = best;
+}
+
+extern "C" int nabo_classify_targets(const int32_t* tgt_knn, const uint8_t* counts, const double* lut, int n_query,
+                                     int k, const int32_t* ref_labels, int n_labels, double weight_frac,
+                                     int min_degree, double min_weight, int32_t* out_label, void* stream) {
+    NABO_ARG(n_query >= 0 && k >= 1, "classify: bad sizes");
+    if (n_query == 0) return 0;
+    NABO_ARG(tgt_knn && counts && lut && ref_labels && out_label, "classify: null pointer");
+    classify_kernel<<<(n_query + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        tgt_knn, counts, lut, n_query, k, ref_labels, n_labels, weight_frac, min_degree, min_weight, out_label);
+    NABO_LAUNCH_CHECK("classify_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------ shard merge
+__global__ void __launch_bounds__(128)
+merge_kernel(const int32_t* __restrict__ idx, const double* __restrict__ dist, int n_shards, int n_query, int k,
+             int capp, int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = blockIdx.x * 4 + warp;
+    if (qi >= n_query) return;
+    double* d = smem + (size_t)warp * capp;
+    int* ix = (int*)(smem + (size_t)4 * capp) + (size_t)warp * capp;
+    const int tot = n_shards * k;
+    for (int c = lane; c < capp; c += 32) {
+        double dv = CUDART_INF;
+        int id = 0x7fffffff;
+        if (c < tot) {
+            const int s = c / k, j = c - s * k;
+            const long long off = ((long long)s * n_query + qi) * k + j;
+            const int i0 = idx[off];
+            if (i0 >= 0) {
+                id = i0;
+                dv = dist[off];
+                if (dv != dv) dv = CUDART_INF;
+            }
+        }
+        d[c] = dv; ix[c] = id;
+    }
+    __syncwarp();
+    warp_bitonic_sort(d, ix, capp, lane);
+    for (int t = lane; t < k; t += 32) {
+        int id = ix[t];
+        double dv = d[t];
+        if (id == 0x7fffffff) { id = -1; dv = CUDART_NAN; }
+        else if (dv == CUDART_INF) dv = CUDART_NAN;
+        out_idx[(long long)qi * k + t] = id;
+        out_dist[(long long)qi * k + t] = dv;
+    }
+}
+
+extern "C" int nabo_merge_topk(const int32_t* idx, const double* dist, int n_shards, int n_query, int k,
+                               int32_t* out_idx, double* out_dist, void* stream) {
+    NABO_ARG(n_shards >= 1 && k >= 1 && n_query >= 0, "merge: bad sizes");
+    NABO_ARG((long long)n_shards * k <= 2048, "merge: n_shards*k=%d exceeds 2048", n_shards * k);
+    if (n_query == 0) return 0;
+    NABO_ARG(idx && dist && out_idx && out_dist, "merge: null pointer");
+    int capp = nabo_next_pow2(n_shards * k);
+    if (capp < 32) capp = 32;
+    size_t smem = (size_t)4 * capp * (sizeof(double) + sizeof(int));
+    NABO_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_kernel<<<(n_query + 3) / 4, 128, smem, (cudaStream_t)stream>>>(idx, dist, n_shards, n_query, k, capp,
+                                                                        out_idx, out_dist);
+    NABO_LAUNCH_CHECK("merge_kernel");
+    return 0;
+}
