@@ -73,14 +73,32 @@ int nabo_cosine_dist(const double* x, int ldx, const double* y, int ldy, double*
  *   idx_offset added to every output index (reference-sharded mode)
  *   out_idx (n_query x k) int32, out_dist (n_query x k) FP64 (NaN for masked /
  *   missing entries, idx -1 when fewer than k references exist)
- *   stats_host optional int64[4]: {rows re-ranked, rows sent to exact fallback,
- *              candidates kept per row, 0}; filled only if non-NULL (forces a sync)
+ *   stats_host optional int64[8], filled only if non-NULL (forces a stream sync at the
+ *              end of the call): [0] rows re-ranked, [1] rows sent to the exact
+ *              brute-force engine, [2] candidates kept per row, [3] kernels launched,
+ *              [4] ns spent in the dominant distance/top-k kernel (CUDA events on
+ *              `stream`), [5] ns in the exact re-rank, [6] ns in the exact fallback,
+ *              [7] ns in operand preparation.
  */
 size_t nabo_knn_workspace_bytes(int n_query, int n_ref, int g, int k, int metric, int mode);
 int nabo_knn(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
              int k, int metric, double dist_factor, const uint8_t* ref_mask, int drop_first,
              int idx_offset, int mode, int32_t* out_idx, double* out_dist, void* workspace,
              size_t workspace_bytes, int64_t* stats_host, void* stream);
+
+/* Candidate pass alone (Euclidean / cosine): TMA-fed tcgen05 GEMM with a fused
+ * per-query top-K' filter.  out_cand (n_query x K') LOCAL reference indices sorted by
+ * candidate score (-1 = empty), K' = nabo_knn_candidates_width(k, drop_first);
+ * out_tau (n_query) = score threshold every non-candidate is at or above (+inf = no
+ * reference was rejected); optional out_qn2 (n_query) and out_scal (4 doubles: scale,
+ * 1/scale, max scaled reference norm, cosine flag) are what the certificate uses.
+ * nabo_knn(mode = NABO_MODE_FAST) = this + nabo_rerank_exact + certificate + fallback. */
+int nabo_knn_candidates_width(int k, int drop_first);
+size_t nabo_knn_candidates_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_first);
+int nabo_knn_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref,
+                        int g, int k, int metric, const uint8_t* ref_mask, int drop_first,
+                        int32_t* out_cand, float* out_tau, double* out_qn2, double* out_scal,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Exact re-rank of caller-supplied candidates (cand: n_query x n_cand int32 LOCAL
  * reference indices, -1 = empty) in the reference's arithmetic; writes the best k. */

@@ -36,6 +36,9 @@ SIGNATURES: Dict[str, tuple] = {
     "nabo_knn_workspace_bytes": (_z, [_i, _i, _i, _i, _i, _i]),
     "nabo_knn": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _d, _p, _i, _i, _i, _p, _p, _p, _z,
                       C.POINTER(C.c_int64), _p]),
+    "nabo_knn_candidates_width": (_i, [_i, _i]),
+    "nabo_knn_candidates_workspace_bytes": (_z, [_i, _i, _i, _i, _i]),
+    "nabo_knn_candidates": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _z, _p]),
     "nabo_rerank_exact": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _d, _p, _i, _i, _p, _i, _p, _p, _p]),
     "nabo_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "nabo_snn_weights": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p]),

@@ -17,7 +17,7 @@ import torch
 from . import _lib
 from ._lib import METRICS, MODE_EXACT, MODE_FAST, check, lib, require_device
 
-__all__ = ["euclidean_dist", "mod_canberra_dist", "cosine_dist", "knn", "rerank_exact", "merge_topk",
+__all__ = ["euclidean_dist", "mod_canberra_dist", "cosine_dist", "knn", "knn_candidates", "rerank_exact", "merge_topk",
            "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets",
            "project", "project_csr", "map_cells", "resolve_metric"]
 
@@ -156,15 +156,40 @@ def knn(q, r, k: int, metric: str = "euclidean", dist_factor: float = 0.25, ref_
     L = lib()
     ws_bytes = int(L.nabo_knn_workspace_bytes(n, m, g, k, METRICS[metric], mode_i))
     ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=qd.device)
-    stats = (C.c_int64 * 4)() if return_stats else None
+    stats = (C.c_int64 * 8)() if return_stats else None
     check(L.nabo_knn(_ptr(qd), g, _ptr(rd), g, n, m, g, k, METRICS[metric], float(dist_factor), _ptr(md),
                      1 if drop_first else 0, int(idx_offset), mode_i, _ptr(idx), _ptr(dst), _ptr(ws),
                      ws.numel(), stats, C.c_void_p(_stream())), "knn")
     res = (_out(idx, host), _out(dst, host))
     if return_stats:
         res = res + ({"rows_reranked": int(stats[0]), "rows_exact_fallback": int(stats[1]),
-                      "candidates_per_row": int(stats[2])},)
+                      "candidates_per_row": int(stats[2]), "kernel_launches": int(stats[3]),
+                      "main_kernel_ms": stats[4] / 1e6, "rerank_ms": stats[5] / 1e6,
+                      "fallback_ms": stats[6] / 1e6, "prep_ms": stats[7] / 1e6},)
     return res
+
+
+def knn_candidates(q, r, k: int, metric: str = "euclidean", ref_mask=None, drop_first: bool = False):
+    """Tensor-core candidate pass alone (Euclidean / cosine).  Returns dict(cand int32 (N,K'),
+    tau float32 (N,), qn2 float64 (N,), scal float64 (4,)); see include/nabo_b200.h."""
+    require_device()
+    host = _is_host(q, r)
+    qd, rd = _dev(q, torch.float64), _dev(r, torch.float64)
+    n, g = qd.shape
+    m = rd.shape[0]
+    md = _mask_dev(ref_mask)
+    L = lib()
+    kp = int(L.nabo_knn_candidates_width(int(k), 1 if drop_first else 0))
+    cand = torch.empty((n, kp), dtype=torch.int32, device=qd.device)
+    tau = torch.empty(n, dtype=torch.float32, device=qd.device)
+    qn2 = torch.empty(n, dtype=torch.float64, device=qd.device)
+    scal = torch.empty(4, dtype=torch.float64, device=qd.device)
+    ws = torch.empty(int(L.nabo_knn_candidates_workspace_bytes(n, m, g, int(k), 1 if drop_first else 0)),
+                     dtype=torch.uint8, device=qd.device)
+    check(L.nabo_knn_candidates(_ptr(qd), g, _ptr(rd), g, n, m, g, int(k), METRICS[metric], _ptr(md),
+                                1 if drop_first else 0, _ptr(cand), _ptr(tau), _ptr(qn2), _ptr(scal), _ptr(ws),
+                                ws.numel(), C.c_void_p(_stream())), "knn_candidates")
+    return {"cand": _out(cand, host), "tau": _out(tau, host), "qn2": _out(qn2, host), "scal": _out(scal, host)}
 
 
 def rerank_exact(q, r, cand, k: int, metric: str = "euclidean", dist_factor: float = 0.25, ref_mask=None,

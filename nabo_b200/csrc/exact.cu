@@ -11,6 +11,7 @@
 #include <stdio.h>
 
 #include "common.cuh"
+#include "knn_internal.cuh"
 
 // ------------------------------------------------------------------ error channel
 static thread_local char g_err[512] = "";
@@ -380,33 +381,50 @@ int nabo_knn_exact_launch(const double* q, int ldq, const double* r, int ldr, in
 }
 
 // ------------------------------------------------------------------ exact re-rank of candidates
-// One warp per query.  cand (n_query x n_cand) holds LOCAL reference indices, -1 = empty.
-// If cert_tau != nullptr the kernel also evaluates the candidate certificate: the k-th
-// exact score must lie strictly below cert_tau[q] - cert_eps[q] (both in the SCORE space of
-// the candidate pass: squared distance for Euclidean, distance otherwise); rows that fail
-// are appended to fail_rows (count in fail_count) for the exact fallback.
+// One warp per query.  cand (n_query x n_cand) holds LOCAL reference indices, -1 = empty,
+// all distinct.  With a certificate (NaboCert.kind != 0) the kernel also proves that no
+// reference outside the candidate list can belong to the top ksel: every such reference
+// had candidate-pass score >= tau[q], which bounds its exact distance from below by L(q);
+// the row passes iff its ksel-th exact distance is strictly below L(q).  Rows that fail are
+// appended to fail_rows for the exact brute-force engine.
+__device__ __forceinline__ double cert_lower_bound(const NaboCert& c, int qi, float tau) {
+    const double sc_inv = c.scal[1], rmax = c.scal[2];
+    if (c.kind == NABO_CERT_LINEAR) return (double)tau - c.c_acc;
+    const double qn2 = c.qn2[qi];
+    const double qn = sqrt(qn2);
+    const double eps = c.c_acc * (4.0 * qn * rmax + rmax * rmax + qn2);       // accumulation error (scaled^2)
+    const double l2 = (double)tau + qn2 - eps;
+    if (!(l2 > 0.0)) return 0.0;
+    if (c.kind == NABO_CERT_EUCLID) {
+        // |d~ - d| <= 2^-21 (|q| + |r|) from the two-term FP16 split of the inputs
+        return sqrt(l2) * sc_inv * (1.0 - 1e-7) - 9.6e-7 * (qn + rmax) * sc_inv;
+    }
+    // cosine: unit vectors, chord e -> distance e^2 / 2
+    double e = sqrt(l2) * sc_inv - 1.0e-6;
+    if (!(e > 0.0)) return 0.0;
+    return 0.5 * e * e * (1.0 - 1e-9);
+}
+
 template <int METRIC>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ r, int ldr, int n_query,
               int n_ref, int g, int k, double f, const uint8_t* __restrict__ mask, int drop_first,
-              int idx_offset, const int32_t* __restrict__ cand, int n_cand, int capp,
-              const float* __restrict__ cert_tau, const float* __restrict__ cert_eps,
+              int idx_offset, const int32_t* __restrict__ cand, int n_cand, int capp, const NaboCert cert,
               int* __restrict__ fail_rows, int* __restrict__ fail_count,
               int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x * 4 + warp;
     if (qi >= n_query) return;
-    double* d = smem + (size_t)warp * capp * 2;           // keys (final distance)
-    double* sc = d + capp;                                  // scores (pre-sqrt for Euclidean)
-    int* ix = (int*)(smem + (size_t)4 * capp * 2) + (size_t)warp * capp;
+    double* d = smem + (size_t)warp * capp;
+    int* ix = (int*)(smem + (size_t)4 * capp) + (size_t)warp * capp;
     const double* x = q + (long long)qi * ldq;
     double nq = 0.0;
     if (METRIC == NABO_COSINE) nq = seq_sqnorm(x, g);
-    int n_valid = 0;
+    int n_valid = 0, n_finite = 0;
     for (int c = lane; c < capp; c += 32) {
         int j = c < n_cand ? cand[(long long)qi * n_cand + c] : -1;
-        double key = CUDART_INF, score = CUDART_INF;
+        double key = CUDART_INF;
         int id = 0x7fffffff;
         if (j >= 0 && j < n_ref) {
             const double* y = r + (long long)j * ldr;
@@ -415,29 +433,19 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
             double nr = 0.0;
             if (METRIC == NABO_COSINE) nr = seq_sqnorm(y, g);
             double dv = Pair<METRIC>::finish(acc, nq, nr);
-            score = METRIC == NABO_EUCLIDEAN ? acc : dv;
-            if (dv != dv || (mask && mask[j])) { dv = CUDART_INF; score = CUDART_INF; }
+            if (dv != dv || (mask && mask[j])) dv = CUDART_INF;
             key = dv;
             id = j;
+            ++n_valid;
+            n_finite += (dv < CUDART_INF);
         }
-        d[c] = key; sc[c] = score; ix[c] = id;
-        n_valid += (id != 0x7fffffff);
+        d[c] = key; ix[c] = id;
     }
     __syncwarp();
-    for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
-    // sort by (key, idx); scores follow their keys (monotone map, so recompute from position is
-    // unnecessary: carry them through a second pass keyed by idx lookup)
-    // -> simple approach: sort (key, idx), then fetch score of the k-th entry by searching ix.
-    // Keep a copy of unsorted (idx, score) in registers of the owning lanes.
-    int my_id[4];
-    double my_sc[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        int c = lane + 32 * u;
-        my_id[u] = c < capp ? ix[c] : 0x7fffffff;
-        my_sc[u] = c < capp ? sc[c] : CUDART_INF;
+    for (int o = 16; o > 0; o >>= 1) {
+        n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+        n_finite += __shfl_xor_sync(0xffffffffu, n_finite, o);
     }
-    __syncwarp();
     warp_bitonic_sort(d, ix, capp, lane);
     const int skip = drop_first ? 1 : 0;
     const int ksel = k + skip;
@@ -454,45 +462,31 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
         out_idx[(long long)qi * k + t] = id;
         out_dist[(long long)qi * k + t] = dv;
     }
-    if (cert_tau) {
-        // score of the ksel-th best candidate
+    if (cert.kind != NABO_CERT_NONE && lane == 0) {
+        const float tau = cert.tau[qi];
         bool fail;
-        if (n_valid < ksel) {
-            // fewer candidates than needed: only acceptable when nothing was rejected
-            fail = !(cert_tau[qi] == CUDART_INF_F);
-        } else {
-            int kid = ix[ksel - 1];
-            double ks = CUDART_INF;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (my_id[u] == kid) ks = my_sc[u];
-            for (int o = 16; o > 0; o >>= 1) ks = fmin(ks, __shfl_xor_sync(0xffffffffu, ks, o));
-            double bound = (double)cert_tau[qi] - (double)cert_eps[qi];
-            fail = !(ks < bound);
-            if (cert_tau[qi] == CUDART_INF_F) fail = false;   // nothing was rejected
-        }
-        if (fail && lane == 0) {
-            int p = atomicAdd(fail_count, 1);
-            fail_rows[p] = qi;
-        }
+        if (tau == CUDART_INF_F) fail = n_valid < n_ref;          // nothing rejected <=> every reference is a candidate
+        else if (n_finite < ksel) fail = true;
+        else fail = !(d[ksel - 1] < cert_lower_bound(cert, qi, tau));
+        if (fail) fail_rows[atomicAdd(fail_count, 1)] = qi;
     }
 }
 
 int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
-                       const int32_t* cand, int n_cand, const float* cert_tau, const float* cert_eps,
-                       int* fail_rows, int* fail_count, int32_t* out_idx, double* out_dist, cudaStream_t st) {
+                       const int32_t* cand, int n_cand, const NaboCert& cert, int* fail_rows, int* fail_count,
+                       int32_t* out_idx, double* out_dist, cudaStream_t st) {
     NABO_ARG(n_cand >= 1 && n_cand <= 128, "rerank: n_cand=%d unsupported (1..128)", n_cand);
     NABO_ARG(k >= 1 && k + (drop_first ? 1 : 0) <= n_cand, "rerank: k=%d does not fit n_cand=%d", k, n_cand);
     if (n_query == 0) return 0;
     int capp = nabo_next_pow2(n_cand);
     if (capp < 32) capp = 32;
-    size_t smem = (size_t)4 * capp * (2 * sizeof(double) + sizeof(int));
+    size_t smem = (size_t)4 * capp * (sizeof(double) + sizeof(int));
     dim3 grid((n_query + 3) / 4);
 #define LAUNCH(M)                                                                                              \
     rerank_kernel<M><<<grid, 128, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first,       \
-                                              idx_offset, cand, n_cand, capp, cert_tau, cert_eps, fail_rows,   \
-                                              fail_count, out_idx, out_dist);
+                                              idx_offset, cand, n_cand, capp, cert, fail_rows, fail_count,     \
+                                              out_idx, out_dist);
     if (metric == NABO_EUCLIDEAN) { LAUNCH(NABO_EUCLIDEAN) }
     else if (metric == NABO_MOD_CANBERRA) { LAUNCH(NABO_MOD_CANBERRA) }
     else if (metric == NABO_COSINE) { LAUNCH(NABO_COSINE) }
@@ -508,7 +502,9 @@ extern "C" int nabo_rerank_exact(const double* q, int ldq, const double* r, int 
                                  int32_t* out_idx, double* out_dist, void* stream) {
     NABO_ARG(q && r && cand && out_idx && out_dist, "rerank: null pointer");
     NABO_ARG(ldq >= g && ldr >= g, "rerank: leading dimension smaller than g");
+    NaboCert none;
+    none.kind = NABO_CERT_NONE; none.tau = nullptr; none.qn2 = nullptr; none.scal = nullptr; none.c_acc = 0.0;
     return nabo_rerank_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, dist_factor, ref_mask, drop_first,
-                              idx_offset, cand, n_cand, nullptr, nullptr, nullptr, nullptr, out_idx, out_dist,
+                              idx_offset, cand, n_cand, none, nullptr, nullptr, out_idx, out_dist,
                               (cudaStream_t)stream);
 }

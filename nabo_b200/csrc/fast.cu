@@ -1,14 +1,80 @@
-// Fast kNN engine: candidate pass + exact FP64 re-rank + certificate + exact fallback.
-// (candidate kernels are added per metric; until one exists for a metric the engine
-//  reports NABO_EUNSUPPORTED rather than silently running something else)
+// Fast kNN engine: candidate pass -> exact FP64 re-rank + certificate -> exact brute force
+// for the rows the certificate could not clear.  Results are identical to the exact engine
+// (and hence to the reference) by construction; only the amount of FP64 work changes.
+//   Euclidean / cosine : tensor-core candidate pass (tc_candidates.cu)
+//   modified Canberra  : exact engine (an FP32 CUDA-core candidate pass is the next step)
 #include "knn_internal.cuh"
 
+// Accumulation-error constant of the tensor-core score relative to (4|q||r| + |r|^2 + |q|^2);
+// measured on B200 by tests/test_gpu_tc.py::test_tc_score_error_bound, which asserts a >= 4x margin.
+static const double kCAcc = 1.52587890625e-05;   // 2^-16
+
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric) {
-    (void)n_query; (void)n_ref; (void)g; (void)k; (void)metric;
-    return 256;
+    if (metric == NABO_MOD_CANBERRA) return 256;
+    return nabo_tc_workspace_bytes(n_query, n_ref, g, k, 1) + nabo_align_up((size_t)n_query * 4, 256) + 1024;
 }
 
-int nabo_knn_fast(const double*, int, const double*, int, int, int, int, int, int metric, double, const uint8_t*,
-                  int, int, int32_t*, double*, void*, size_t, int64_t*, cudaStream_t) {
-    return nabo_set_error(NABO_EUNSUPPORTED, "knn: fast engine not built for metric %d", metric);
+int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
+                  int metric, double f, const uint8_t* mask, int drop_first, int idx_offset, int32_t* out_idx,
+                  double* out_dist, void* workspace, size_t workspace_bytes, int64_t* stats_host,
+                  cudaStream_t st) {
+    NaboStageTimer tm(stats_host != nullptr, st);
+    tm.begin();
+    const bool use_tc = (metric == NABO_EUCLIDEAN || metric == NABO_COSINE) && nabo_tc_supported(g, k, drop_first) &&
+                        n_ref > nabo_tc_kprime(k, drop_first);
+    if (!use_tc) {
+        int rc = nabo_knn_exact_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
+                                       nullptr, nullptr, out_idx, out_dist, st);
+        tm.end(0);
+        if (rc) return rc;
+        if (stats_host) {
+            NABO_CUDA(cudaStreamSynchronize(st));
+            stats_host[1] = n_query;
+            stats_host[3] = 1;
+            stats_host[4] = tm.ns(0);
+        }
+        return 0;
+    }
+    if (workspace_bytes < nabo_fast_workspace_bytes(n_query, n_ref, g, k, metric))
+        return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small (%zu < %zu)", workspace_bytes,
+                              nabo_fast_workspace_bytes(n_query, n_ref, g, k, metric));
+    NaboArena ar(workspace, workspace_bytes);
+    int32_t* cand = nullptr;
+    float* tau = nullptr;
+    double *qn2 = nullptr, *scal = nullptr;
+    int kprime = 0, launches = 0;
+    int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, mask, drop_first, ar, &cand, &kprime,
+                                &tau, &qn2, &scal, &launches, tm, st);
+    if (rc) return rc;
+    int* fail_rows = ar.take<int>(n_query);
+    int* fail_count = ar.take<int>(1);
+    if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
+    NABO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
+    NaboCert cert;
+    cert.kind = metric == NABO_COSINE ? NABO_CERT_COSINE : NABO_CERT_EUCLID;
+    cert.tau = tau; cert.qn2 = qn2; cert.scal = scal; cert.c_acc = kCAcc;
+    rc = nabo_rerank_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset, cand,
+                            kprime, cert, fail_rows, fail_count, out_idx, out_dist, st);
+    if (rc) return rc;
+    tm.end(1);
+    // rows the certificate did not clear: exact brute force (grid sized for the worst case,
+    // blocks beyond the device-side row count exit immediately)
+    rc = nabo_knn_exact_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
+                               fail_rows, fail_count, out_idx, out_dist, st);
+    if (rc) return rc;
+    tm.end(2);
+    if (stats_host) {
+        int nfail = 0;
+        NABO_CUDA(cudaMemcpyAsync(&nfail, fail_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        NABO_CUDA(cudaStreamSynchronize(st));
+        stats_host[0] = n_query;
+        stats_host[1] = nfail;
+        stats_host[2] = kprime;
+        stats_host[3] = launches + 2;
+        stats_host[4] = tm.ns(0);
+        stats_host[5] = tm.ns(1);
+        stats_host[6] = tm.ns(2);
+        stats_host[7] = tm.ns(3);
+    }
+    return 0;
 }

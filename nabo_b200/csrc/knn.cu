@@ -21,12 +21,21 @@ extern "C" int nabo_knn(const double* q, int ldq, const double* r, int ldr, int 
     NABO_ARG(metric != NABO_MOD_CANBERRA || dist_factor > 0.0, "knn: dist_factor must be > 0");
     if (n_query == 0) return 0;
     NABO_ARG(q && r && out_idx && out_dist, "knn: null pointer");
-    if (stats_host) { stats_host[0] = stats_host[1] = stats_host[2] = stats_host[3] = 0; }
+    if (stats_host) for (int i = 0; i < 8; ++i) stats_host[i] = 0;
     if (mode == NABO_MODE_EXACT) {
+        NaboStageTimer tm(stats_host != nullptr, st);
+        tm.begin();
         int rc = nabo_knn_exact_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, dist_factor, ref_mask,
                                        drop_first, idx_offset, nullptr, nullptr, out_idx, out_dist, st);
-        if (rc == 0 && stats_host) stats_host[1] = n_query;
-        return rc;
+        tm.end(0);
+        if (rc) return rc;
+        if (stats_host) {
+            NABO_CUDA(cudaStreamSynchronize(st));
+            stats_host[1] = n_query;
+            stats_host[3] = 1;
+            stats_host[4] = tm.ns(0);
+        }
+        return 0;
     }
     NABO_ARG(mode == NABO_MODE_FAST, "knn: unknown mode %d", mode);
     return nabo_knn_fast(q, ldq, r, ldr, n_query, n_ref, g, k, metric, dist_factor, ref_mask, drop_first,

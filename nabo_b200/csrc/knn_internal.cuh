@@ -7,13 +7,75 @@ int nabo_knn_exact_launch(const double* q, int ldq, const double* r, int ldr, in
                           const int* row_ids, const int* n_rows_dev, int32_t* out_idx, double* out_dist,
                           cudaStream_t st);
 
+// Candidate certificate evaluated by the re-rank (see rerank_kernel).
+#define NABO_CERT_NONE 0
+#define NABO_CERT_EUCLID 1   // L = sqrt(tau + |q~|^2 - eps) / sc - slack
+#define NABO_CERT_COSINE 2   // chord on unit vectors -> e^2 / 2
+#define NABO_CERT_LINEAR 3   // L = tau - c_acc  (candidate score is a lower bound of the distance)
+struct NaboCert {
+    int kind;
+    const float* tau;      // [n_query] final candidate threshold (score space), +inf = nothing rejected
+    const double* qn2;     // [n_query] |q~|^2 in scaled units (Euclid / cosine)
+    const double* scal;    // {sc, 1/sc, max scaled reference norm, cosine flag}
+    double c_acc;          // accumulation-error constant (Euclid / cosine) or absolute slack (linear)
+};
+
 int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
-                       const int32_t* cand, int n_cand, const float* cert_tau, const float* cert_eps,
-                       int* fail_rows, int* fail_count, int32_t* out_idx, double* out_dist, cudaStream_t st);
+                       const int32_t* cand, int n_cand, const NaboCert& cert, int* fail_rows, int* fail_count,
+                       int32_t* out_idx, double* out_dist, cudaStream_t st);
+
+struct NaboStageTimer;
+bool nabo_tc_supported(int g, int k, int drop_first);
+int nabo_tc_kprime(int k, int drop_first);
+size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_first);
+int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
+                       int metric, const uint8_t* mask, int drop_first, NaboArena& ar, int32_t** cand_idx_out,
+                       int* kprime_out, float** cert_tau_out, double** qn2_out, double** scal_out, int* launches,
+                       NaboStageTimer& tm, cudaStream_t st);
 
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric);
 int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                   int metric, double f, const uint8_t* mask, int drop_first, int idx_offset, int32_t* out_idx,
                   double* out_dist, void* workspace, size_t workspace_bytes, int64_t* stats_host,
                   cudaStream_t st);
+
+// CUDA-event stage timer, active only when the caller asked for stats (stats_host != NULL).
+// Usage: begin(); <launch stage 0>; end(0); <launch stage 1>; end(1); ... sync; ns(i).
+struct NaboStageTimer {
+    static constexpr int MAXS = 4;
+    bool on;
+    cudaStream_t st;
+    cudaEvent_t start;
+    cudaEvent_t stop[MAXS];
+    int prev[MAXS];
+    bool used[MAXS];
+    int last;
+    NaboStageTimer(bool enable, cudaStream_t s) : on(enable), st(s), last(-1) {
+        for (int i = 0; i < MAXS; ++i) { prev[i] = -1; used[i] = false; }
+        if (on) {
+            cudaEventCreate(&start);
+            for (int i = 0; i < MAXS; ++i) cudaEventCreate(&stop[i]);
+        }
+    }
+    ~NaboStageTimer() {
+        if (on) {
+            cudaEventDestroy(start);
+            for (int i = 0; i < MAXS; ++i) cudaEventDestroy(stop[i]);
+        }
+    }
+    void begin() { if (on) cudaEventRecord(start, st); }
+    void end(int i) {          // stage i ran since the previous begin()/end()
+        if (!on) return;
+        cudaEventRecord(stop[i], st);
+        used[i] = true;
+        prev[i] = last;
+        last = i;
+    }
+    long long ns(int i) {      // valid after the stream has been synchronised
+        if (!on || !used[i]) return 0;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, prev[i] < 0 ? start : stop[prev[i]], stop[i]);
+        return (long long)((double)ms * 1e6);
+    }
+};

@@ -1,0 +1,507 @@
+// Tensor-core candidate pass for Euclidean / cosine kNN (sm_100a: TMA bulk copies ->
+// shared memory -> tcgen05.mma -> TMEM -> fused per-query top-K' filter).
+//
+//   score(q, r) = ||r~||^2 - 2 q~.r~        (ranking-equivalent to ||q~ - r~||^2)
+// with q~ = qh + ql, r~ = rh + rl the two-term FP16 split of the (power-of-two scaled)
+// coordinates, evaluated as ONE GEMM with the augmented K dimension
+//   A row (query)     = [-2qh | -2qh | -2ql | 1  1  1  | 0..]
+//   B row (reference) = [  rh |   rl |   rh | n1 n2 n3 | 0..]      n1+n2+n3 = ||r~||^2
+// so the accumulator IS the score and the epilogue is pure selection.  Operands are
+// pre-tiled in HBM in the UMMA K-major no-swizzle core-matrix layout (pack kernels below),
+// so one tile is one contiguous span and a single cp.async.bulk brings it in.
+//
+// CTA = 512 threads, persistent over work items of NQ=3 query tiles (384 queries):
+//   warp 0   TMA producer: A tiles once per item, B (reference) tiles through a ring
+//   warp 1   MMA issuer : per reference tile, NQ x KSTEPS tcgen05.mma into NQ accumulators
+//   warp 2   TMEM allocator
+//   warps 4-15  epilogue: warpgroup w owns query tile w; thread = one query row (TMEM lane)
+// The epilogue keeps, per query, a running threshold tau (register) and a private
+// candidate buffer of CAP keys in L2-resident global memory; a tile chunk is first reduced
+// with FMNMX3 and only chunks holding a score < tau take the append path.  When a buffer
+// may overflow the warp sorts it (bitonic, shared-memory staging), keeps the K' best and
+// tightens tau.  Everything rejected or dropped has score >= final tau, which is what the
+// certificate in the re-rank needs.
+#include "common.cuh"
+#include "knn_internal.cuh"
+#include "ptx.cuh"
+
+#include <cuda_fp16.h>
+
+namespace tc {
+
+constexpr int TILE = 128;           // rows per operand tile (UMMA M and N)
+constexpr int NQ = 3;               // query tiles per work item
+constexpr int NTHREADS = 512;
+constexpr int EPI_WARP0 = 4;
+constexpr int CAP = 128;            // candidate buffer entries per query
+constexpr int CHUNK = 32;           // columns per tcgen05.ld
+
+__host__ __device__ inline int kp_for(int g) { return (3 * g + 3 + 15) / 16 * 16; }
+__host__ __device__ inline size_t tile_bytes(int kp) { return (size_t)TILE * kp * 2; }
+
+struct SmemPlan {
+    int stages;
+    size_t a_off, b_off, sort_off, bar_off, total;
+};
+inline SmemPlan plan_smem(int kp) {
+    SmemPlan p;
+    size_t a = NQ * tile_bytes(kp);
+    size_t sort = (size_t)(NTHREADS / 32 - EPI_WARP0) * CAP * 8;
+    size_t bars = 512;
+    size_t budget = 227 * 1024 - 1024;   // keep 1 KB for alignment slack
+    size_t left = budget > a + sort + bars ? budget - a - sort - bars : 0;
+    p.stages = (int)(left / tile_bytes(kp));
+    if (p.stages > 4) p.stages = 4;
+    p.a_off = 0;
+    p.b_off = a;
+    p.sort_off = a + (size_t)p.stages * tile_bytes(kp);
+    p.bar_off = p.sort_off + sort;
+    p.total = p.bar_off + bars;
+    return p;
+}
+
+// ------------------------------------------------------------------ operand packing
+// norms2[row] = ||x||^2 (FP64, exact coordinates); maxn2 = max finite norm^2 (as float bits)
+__global__ void __launch_bounds__(256)
+norms_kernel(const double* __restrict__ x, int ld, int n, int g, double* __restrict__ norms2,
+             unsigned int* __restrict__ maxn2_bits) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    float mine = 0.f;
+    if (row < n) {
+        const double* p = x + (long long)row * ld;
+        double s = 0.0;
+        for (int k = 0; k < g; ++k) s = fma(p[k], p[k], s);
+        norms2[row] = s;
+        if (isfinite(s)) mine = __double2float_ru(s);
+    }
+    for (int o = 16; o > 0; o >>= 1) mine = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+    if ((threadIdx.x & 31) == 0 && mine > 0.f) atomicMax(maxn2_bits, __float_as_uint(mine));
+}
+
+// scal[0] = sc (power of two), scal[1] = 1/sc, scal[2] = max scaled reference norm, scal[3] = cosine flag
+__global__ void scale_kernel(const unsigned int* __restrict__ maxq_bits, const unsigned int* __restrict__ maxr_bits,
+                             int cosine, double* __restrict__ scal) {
+    double sc = 1.0, rmax;
+    if (cosine) {
+        sc = 32.0;               // unit vectors
+        rmax = 32.0 * (1.0 + 1e-6);
+    } else {
+        float mq = __uint_as_float(*maxq_bits), mr = __uint_as_float(*maxr_bits);
+        double mx = sqrt((double)fmaxf(mq, mr));
+        if (mx > 0.0 && isfinite(mx)) {
+            int e;
+            frexp(mx, &e);        // mx = f * 2^e, f in [0.5, 1)  ->  mx * 2^(6-e) in [32, 64)
+            sc = ldexp(1.0, 6 - e);
+        }
+        rmax = sqrt((double)__uint_as_float(*maxr_bits)) * sc * (1.0 + 1e-6);
+    }
+    scal[0] = sc;
+    scal[1] = 1.0 / sc;
+    scal[2] = rmax;
+    scal[3] = cosine ? 1.0 : 0.0;
+}
+
+// One thread per row; 16-byte chunk kc of row r of tile t lands at
+//   t * TILE*kp*2 + kc * (TILE*16) + (r>>3)*128 + (r&7)*16
+// (core matrices of 8 rows x 16 B, K-chunk-major: SBO = 128 B, LBO = TILE*16 B).
+template <bool IS_QUERY>
+__global__ void __launch_bounds__(TILE)
+pack_kernel(const double* __restrict__ x, int ld, int n, int g, int kp, const double* __restrict__ norms2,
+            const double* __restrict__ scal, const uint8_t* __restrict__ mask, __half* __restrict__ out,
+            double* __restrict__ qn2_out) {
+    const int r = threadIdx.x;
+    const long long row = (long long)blockIdx.x * TILE + r;
+    __half* tile = out + (size_t)blockIdx.x * TILE * kp;
+    const bool live = row < n;
+    const double sc = scal[0];
+    const bool cosine = scal[3] != 0.0;
+    double mul = sc;
+    bool dead = false;          // reference that can never be a neighbour (masked / zero norm under cosine)
+    if (live && cosine) {
+        double nn = sqrt(norms2[row]);
+        if (nn > 0.0 && isfinite(nn)) mul = sc / nn; else { mul = 0.0; dead = true; }
+    }
+    if (live && !IS_QUERY && mask && mask[row]) dead = true;
+    const double* p = x + (live ? row : 0) * (long long)ld;
+    double n2 = 0.0;            // ||x~||^2 of the split value actually fed to the tensor core (scaled units)
+    const int nchunks = kp / 8;
+    for (int kc = 0; kc < nchunks; ++kc) {
+        __align__(16) __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int col = kc * 8 + e;
+            __half v = __float2half(0.f);
+            if (live && col < 3 * g) {
+                const int seg = col / g, k = col - seg * g;
+                const double xv = p[k] * mul;
+                const __half hi = __double2half(xv);
+                const __half lo = __double2half(xv - (double)__half2float(hi));
+                if (seg == 0) { const double t = (double)__half2float(hi) + (double)__half2float(lo); n2 = fma(t, t, n2); }
+                if (IS_QUERY) {
+                    const __half src = seg == 2 ? lo : hi;
+                    v = __float2half(-2.0f * __half2float(src));      // exact: power-of-two scaling
+                } else {
+                    v = seg == 1 ? lo : hi;
+                }
+            } else if (live && col < 3 * g + 3) {
+                if (IS_QUERY) v = __float2half(1.0f);
+            }
+            h[e] = v;
+        }
+        if (!IS_QUERY && live && 3 * g + 3 > kc * 8 && 3 * g < kc * 8 + 8) {
+            // norm pieces n1 + n2 + n3 = ||r~||^2 (n2 is complete here: columns >= 3g come after segment 0)
+            double rem = dead ? 60000.0 : n2;
+            for (int t = 0; t < 3; ++t) {
+                const int col = 3 * g + t;
+                const __half piece = __double2half(rem);
+                rem -= (double)__half2float(piece);
+                if (dead && t > 0) { if (col >= kc * 8 && col < kc * 8 + 8) h[col - kc * 8] = __float2half(0.f); continue; }
+                if (col >= kc * 8 && col < kc * 8 + 8) h[col - kc * 8] = piece;
+            }
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<char*>(tile) + (size_t)kc * (TILE * 16) + (r >> 3) * 128 + (r & 7) * 16) =
+            *reinterpret_cast<const uint4*>(h);
+    }
+    if (IS_QUERY && live && qn2_out) qn2_out[row] = n2;
+}
+
+// ------------------------------------------------------------------ the candidate kernel
+struct Params {
+    const __half* qa;       // packed queries  [n_qtiles_padded][TILE*kp]
+    const __half* rb;       // packed references [n_rtiles][TILE*kp]
+    int n_query, n_ref, kp, n_items, n_rtiles, stages, kprime, kc_out;
+    unsigned long long* cand_buf;   // [gridDim][NQ*TILE][CAP]
+    int32_t* cand_idx;      // [n_query][kc_out]
+    float* cert_tau;        // [n_query]
+    size_t a_off, b_off, sort_off, bar_off;
+};
+
+struct Barriers {
+    uint64_t a_full, a_empty;
+    uint64_t b_full[4], b_empty[4];
+    uint64_t acc_full[NQ], acc_empty[NQ];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ unsigned long long make_key(float score, uint32_t col) {
+    return ((unsigned long long)float_to_sortable(score) << 32) | col;
+}
+
+// warp-cooperative: sort lane `src`'s buffer, keep the best kprime; returns new (cnt, tau) for src
+__device__ __forceinline__ void compact_buffer(unsigned long long* gbuf, int n, unsigned long long* stage, int lane,
+                                               int kprime, int& new_cnt, float& new_tau) {
+    __syncwarp();      // the owner's appends (plain global stores) are ordered before our loads
+#pragma unroll
+    for (int u = 0; u < CAP / 32; ++u) {
+        const int i = lane + 32 * u;
+        stage[i] = i < n ? __ldcg(gbuf + i) : ~0ull;     // read through L2: never a stale L1 line
+    }
+    __syncwarp();
+    warp_bitonic_sort_u64(stage, CAP, lane);
+    if (n >= kprime) {
+        for (int i = lane; i < kprime; i += 32) gbuf[i] = stage[i];
+        new_cnt = kprime;
+        new_tau = sortable_to_float((uint32_t)(stage[kprime - 1] >> 32));
+    } else {
+        for (int i = lane; i < n; i += 32) gbuf[i] = stage[i];
+        new_cnt = n;
+        new_tau = CUDART_INF_F;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + p.bar_off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ksteps = p.kp / 16;
+    const uint32_t a_tile_bytes = (uint32_t)tile_bytes(p.kp);
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(&bars->a_full, 1);
+        ptx::mbar_init(&bars->a_empty, 1);
+        for (int s = 0; s < 4; ++s) { ptx::mbar_init(&bars->b_full[s], 1); ptx::mbar_init(&bars->b_empty[s], 1); }
+        for (int q = 0; q < NQ; ++q) { ptx::mbar_init(&bars->acc_full[q], 1); ptx::mbar_init(&bars->acc_empty[q], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t t = 0, it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+                ptx::mbar_wait(&bars->a_empty, (it & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&bars->a_full, NQ * a_tile_bytes);
+                for (int q = 0; q < NQ; ++q) {
+                    const char* src = reinterpret_cast<const char*>(p.qa) + (size_t)(item * NQ + q) * a_tile_bytes;
+                    char* dst = reinterpret_cast<char*>(smem + p.a_off) + (size_t)q * a_tile_bytes;
+                    for (uint32_t o = 0; o < a_tile_bytes; o += 8192)
+                        ptx::bulk_g2s(dst + o, src + o, min(8192u, a_tile_bytes - o), &bars->a_full);
+                }
+                for (int j = 0; j < p.n_rtiles; ++j, ++t) {
+                    const uint32_t s = t % p.stages, use = t / p.stages;
+                    ptx::mbar_wait(&bars->b_empty[s], (use & 1) ^ 1);
+                    ptx::mbar_arrive_expect_tx(&bars->b_full[s], a_tile_bytes);
+                    const char* src = reinterpret_cast<const char*>(p.rb) + (size_t)j * a_tile_bytes;
+                    char* dst = reinterpret_cast<char*>(smem + p.b_off) + (size_t)s * a_tile_bytes;
+                    for (uint32_t o = 0; o < a_tile_bytes; o += 8192)
+                        ptx::bulk_g2s(dst + o, src + o, min(8192u, a_tile_bytes - o), &bars->b_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_f16(TILE, TILE);
+            const uint32_t lbo = TILE * 16, sbo = 128;
+            uint32_t t = 0, it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+                ptx::mbar_wait(&bars->a_full, it & 1);
+                for (int j = 0; j < p.n_rtiles; ++j, ++t) {
+                    const uint32_t s = t % p.stages, use = t / p.stages;
+                    ptx::mbar_wait(&bars->b_full[s], use & 1);
+                    ptx::tc_fence_after();
+                    const uint32_t b_addr = ptx::smem_u32(smem + p.b_off) + s * a_tile_bytes;
+                    for (int q = 0; q < NQ; ++q) {
+                        ptx::mbar_wait(&bars->acc_empty[q], (t & 1) ^ 1);
+                        ptx::tc_fence_after();
+                        const uint32_t a_addr = ptx::smem_u32(smem + p.a_off) + q * a_tile_bytes;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t ad = ptx::make_smem_desc(a_addr + ks * 2 * lbo, lbo, sbo);
+                            const uint64_t bd = ptx::make_smem_desc(b_addr + ks * 2 * lbo, lbo, sbo);
+                            ptx::mma_f16_ss(tmem_base + q * TILE, ad, bd, idesc, ks > 0 ? 1u : 0u);
+                        }
+                        ptx::mma_commit(&bars->acc_full[q]);
+                    }
+                    ptx::mma_commit(&bars->b_empty[s]);
+                }
+                ptx::mma_commit(&bars->a_empty);
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===================== epilogue: fused top-K' selection =====================
+        const int q = (warp - EPI_WARP0) >> 2;            // query tile of this warpgroup
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
+        const int row = quarter * 32 + lane;
+        unsigned long long* stage = reinterpret_cast<unsigned long long*>(smem + p.sort_off) + (size_t)(warp - EPI_WARP0) * CAP;
+        unsigned long long* mybuf = p.cand_buf + ((size_t)blockIdx.x * NQ * TILE + q * TILE + row) * CAP;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + q * TILE;
+        uint32_t t = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            float tau = CUDART_INF_F;
+            int cnt = 0;
+            for (int j = 0; j < p.n_rtiles; ++j, ++t) {
+                ptx::mbar_wait(&bars->acc_full[q], t & 1);
+                ptx::tc_fence_after();
+                const int col_limit = p.n_ref - j * TILE;        // columns >= col_limit are padding
+#pragma unroll 1
+                for (int c = 0; c < TILE / CHUNK; ++c) {
+                    uint32_t vr[32];
+                    ptx::tmem_ld_32x32(taddr0 + c * CHUNK, vr);
+                    ptx::tmem_ld_wait();
+                    if (c == TILE / CHUNK - 1) {
+                        // accumulator fully read: hand it back to the MMA warp before filtering
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[q]);
+                    }
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vr[i]);
+                    if (col_limit < (c + 1) * CHUNK) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * CHUNK + i >= col_limit) v[i] = CUDART_INF_F;
+                    }
+                    float g4[4];
+#pragma unroll
+                    for (int gi = 0; gi < 4; ++gi) {
+                        const float a = ptx::min3(v[8 * gi], v[8 * gi + 1], v[8 * gi + 2]);
+                        const float b = ptx::min3(v[8 * gi + 3], v[8 * gi + 4], v[8 * gi + 5]);
+                        g4[gi] = ptx::min3(a, b, fminf(v[8 * gi + 6], v[8 * gi + 7]));
+                    }
+                    const float m = fminf(fminf(g4[0], g4[1]), fminf(g4[2], g4[3]));
+                    if (m < tau) {
+                        const uint32_t col0 = (uint32_t)(j * TILE + c * CHUNK);
+#pragma unroll
+                        for (int gi = 0; gi < 4; ++gi) {
+                            if (g4[gi] < tau) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    if (v[8 * gi + i] < tau) {
+                                        mybuf[cnt] = make_key(v[8 * gi + i], col0 + 8 * gi + i);
+                                        ++cnt;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - CHUNK);
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        unsigned long long* gb = reinterpret_cast<unsigned long long*>(
+                            __shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
+                        const int n = __shfl_sync(0xffffffffu, cnt, src);
+                        int nc;
+                        float nt;
+                        compact_buffer(gb, n, stage, lane, p.kprime, nc, nt);
+                        if (lane == src) { cnt = nc; tau = nt; }
+                    }
+                }
+            }
+            // item done: final compaction of every query of this warp, emit candidates + threshold
+            for (int src = 0; src < 32; ++src) {
+                unsigned long long* gb = reinterpret_cast<unsigned long long*>(
+                    __shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
+                const int n = __shfl_sync(0xffffffffu, cnt, src);
+                const float old_tau = __shfl_sync(0xffffffffu, tau, src);
+                int nc;
+                float nt;
+                compact_buffer(gb, n, stage, lane, p.kprime, nc, nt);
+                const long long qg = (long long)item * NQ * TILE + q * TILE + quarter * 32 + src;
+                if (qg < p.n_query) {
+                    for (int i = lane; i < p.kc_out; i += 32)
+                        p.cand_idx[qg * p.kc_out + i] = i < nc ? (int32_t)(uint32_t)(stage[i] & 0xffffffffull) : -1;
+                    if (lane == 0) p.cert_tau[qg] = n >= p.kprime ? nt : old_tau;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------ host side
+bool nabo_tc_supported(int g, int k, int drop_first) {
+    if (g < 1) return false;
+    const int kp = tc::kp_for(g);
+    const tc::SmemPlan pl = tc::plan_smem(kp);
+    const int ksel = k + (drop_first ? 1 : 0);
+    return pl.stages >= 2 && ksel + 8 <= tc::CAP - tc::CHUNK;
+}
+
+int nabo_tc_kprime(int k, int drop_first) {
+    const int ksel = k + (drop_first ? 1 : 0);
+    int kprime = ksel + (ksel / 4 > 8 ? ksel / 4 : 8);
+    if (kprime > tc::CAP - tc::CHUNK) kprime = tc::CAP - tc::CHUNK;
+    return kprime;
+}
+
+static int tc_grid(int n_items) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return n_items < sms ? n_items : sms;
+}
+
+size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_first) {
+    const int kp = tc::kp_for(g);
+    const size_t tb = tc::tile_bytes(kp);
+    const int n_items = (n_query + tc::NQ * tc::TILE - 1) / (tc::NQ * tc::TILE);
+    const int n_rtiles = (n_ref + tc::TILE - 1) / tc::TILE;
+    const int kprime = nabo_tc_kprime(k, drop_first);
+    size_t b = 0;
+    b += nabo_align_up((size_t)n_items * tc::NQ * tb, 256);          // packed queries
+    b += nabo_align_up((size_t)n_rtiles * tb, 256);                   // packed references
+    b += nabo_align_up((size_t)n_query * 8, 256) * 2;                 // q norms, qn2
+    b += nabo_align_up((size_t)n_ref * 8, 256);                       // r norms
+    b += nabo_align_up((size_t)148 * tc::NQ * tc::TILE * tc::CAP * 8, 256);   // candidate buffers
+    b += nabo_align_up((size_t)n_query * kprime * 4, 256);            // candidate indices
+    b += nabo_align_up((size_t)n_query * 4, 256) * 2;                 // cert tau, fail rows
+    b += 4096;
+    return b;
+}
+
+// Runs norms -> scale -> pack -> candidate kernel.  Outputs (device, inside the arena):
+// cand_idx [n_query][kprime], cert_tau [n_query], qn2 [n_query], scal[4].
+int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
+                       int metric, const uint8_t* mask, int drop_first, NaboArena& ar, int32_t** cand_idx_out,
+                       int* kprime_out, float** cert_tau_out, double** qn2_out, double** scal_out, int* launches,
+                       NaboStageTimer& tm, cudaStream_t st) {
+    const int kp = tc::kp_for(g);
+    const tc::SmemPlan pl = tc::plan_smem(kp);
+    const size_t tb = tc::tile_bytes(kp);
+    const int n_items = (n_query + tc::NQ * tc::TILE - 1) / (tc::NQ * tc::TILE);
+    const int n_qtiles = n_items * tc::NQ;
+    const int n_rtiles = (n_ref + tc::TILE - 1) / tc::TILE;
+    const int kprime = nabo_tc_kprime(k, drop_first);
+    const int grid = tc_grid(n_items);
+
+    __half* qa = (__half*)ar.take<char>((size_t)n_qtiles * tb);
+    __half* rb = (__half*)ar.take<char>((size_t)n_rtiles * tb);
+    double* qnorm = ar.take<double>(n_query);
+    double* qn2 = ar.take<double>(n_query);
+    double* rnorm = ar.take<double>(n_ref);
+    unsigned long long* cbuf = ar.take<unsigned long long>((size_t)grid * tc::NQ * tc::TILE * tc::CAP);
+    int32_t* cand = ar.take<int32_t>((size_t)n_query * kprime);
+    float* tau = ar.take<float>(n_query);
+    double* scal = ar.take<double>(4);
+    unsigned int* maxbits = ar.take<unsigned int>(2);
+    if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small for the tensor-core pass");
+
+    NABO_CUDA(cudaMemsetAsync(maxbits, 0, 2 * sizeof(unsigned int), st));
+    tc::norms_kernel<<<(n_query + 255) / 256, 256, 0, st>>>(q, ldq, n_query, g, qnorm, maxbits);
+    tc::norms_kernel<<<(n_ref + 255) / 256, 256, 0, st>>>(r, ldr, n_ref, g, rnorm, maxbits + 1);
+    tc::scale_kernel<<<1, 1, 0, st>>>(maxbits, maxbits + 1, metric == NABO_COSINE ? 1 : 0, scal);
+    tc::pack_kernel<true><<<n_qtiles, tc::TILE, 0, st>>>(q, ldq, n_query, g, kp, qnorm, scal, nullptr, qa, qn2);
+    tc::pack_kernel<false><<<n_rtiles, tc::TILE, 0, st>>>(r, ldr, n_ref, g, kp, rnorm, scal, mask, rb, nullptr);
+    NABO_LAUNCH_CHECK("tc pack kernels");
+    tm.end(3);
+
+    tc::Params p;
+    p.qa = qa; p.rb = rb;
+    p.n_query = n_query; p.n_ref = n_ref; p.kp = kp; p.n_items = n_items; p.n_rtiles = n_rtiles;
+    p.stages = pl.stages; p.kprime = kprime; p.kc_out = kprime;
+    p.cand_buf = cbuf; p.cand_idx = cand; p.cert_tau = tau;
+    p.a_off = pl.a_off; p.b_off = pl.b_off; p.sort_off = pl.sort_off; p.bar_off = pl.bar_off;
+    NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+    tc::candidates_kernel<<<grid, tc::NTHREADS, pl.total, st>>>(p);
+    NABO_LAUNCH_CHECK("candidates_kernel");
+    tm.end(0);
+    *cand_idx_out = cand; *kprime_out = kprime; *cert_tau_out = tau; *qn2_out = qn2; *scal_out = scal;
+    *launches += 6;
+    return 0;
+}
+
+// ------------------------------------------------------------------ public candidate-pass entry points
+extern "C" int nabo_knn_candidates_width(int k, int drop_first) { return nabo_tc_kprime(k, drop_first); }
+
+extern "C" size_t nabo_knn_candidates_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_first) {
+    return nabo_tc_workspace_bytes(n_query, n_ref, g, k, drop_first);
+}
+
+extern "C" int nabo_knn_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
+                                   int k, int metric, const uint8_t* ref_mask, int drop_first, int32_t* out_cand,
+                                   float* out_tau, double* out_qn2, double* out_scal, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    NABO_ARG(metric == NABO_EUCLIDEAN || metric == NABO_COSINE, "candidates: metric %d has no tensor-core pass", metric);
+    NABO_ARG(n_query >= 1 && n_ref >= 1 && ldq >= g && ldr >= g, "candidates: bad sizes");
+    NABO_ARG(q && r && out_cand && out_tau, "candidates: null pointer");
+    if (!nabo_tc_supported(g, k, drop_first))
+        return nabo_set_error(NABO_EUNSUPPORTED, "candidates: g=%d k=%d outside the tensor-core tile plan", g, k);
+    NaboArena ar(workspace, workspace_bytes);
+    NaboStageTimer tm(false, st);
+    int32_t* cand = nullptr;
+    float* tau = nullptr;
+    double *qn2 = nullptr, *scal = nullptr;
+    int kprime = 0, launches = 0;
+    int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, ref_mask, drop_first, ar, &cand, &kprime,
+                                &tau, &qn2, &scal, &launches, tm, st);
+    if (rc) return rc;
+    NABO_CUDA(cudaMemcpyAsync(out_cand, cand, sizeof(int32_t) * (size_t)n_query * kprime, cudaMemcpyDeviceToDevice, st));
+    NABO_CUDA(cudaMemcpyAsync(out_tau, tau, sizeof(float) * (size_t)n_query, cudaMemcpyDeviceToDevice, st));
+    if (out_qn2) NABO_CUDA(cudaMemcpyAsync(out_qn2, qn2, sizeof(double) * (size_t)n_query, cudaMemcpyDeviceToDevice, st));
+    if (out_scal) NABO_CUDA(cudaMemcpyAsync(out_scal, scal, sizeof(double) * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}

@@ -1,0 +1,114 @@
+"""Tensor-core candidate pass (tcgen05) + certificate: the fast engine must return exactly
+what the exact engine (and the oracle) returns, and the certificate constant must hold."""
+import numpy as np
+import pytest
+
+from oracle import nabo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def core():
+    from nabo_b200 import build, core as c
+    build.build()
+    return c
+
+
+def same_bits(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and bool(((a == b) | (np.isnan(a) & np.isnan(b))).all())
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+@pytest.mark.parametrize("n,m,g,k", [(3000, 20000, 50, 30), (500, 1300, 25, 10), (1000, 5000, 15, 64), (129, 385, 52, 5)])
+def test_fast_equals_exact(core, metric, n, m, g, k):
+    from nabo_b200 import synth
+    q = synth.pc_mixture(n, g, seed=101)
+    r = synth.pc_mixture(m, g, seed=1)
+    fi, fd, st = core.knn(q, r, k, metric, mode="fast", return_stats=True)
+    ei, ed = core.knn(q, r, k, metric, mode="exact")
+    assert same_bits(fd, ed) and np.array_equal(fi, ei)
+    assert st["rows_reranked"] == n
+    assert st["rows_exact_fallback"] <= max(2, n // 50), st     # the certificate clears almost every row
+
+
+def test_fast_self_knn_with_duplicates(core):
+    from nabo_b200 import synth
+    r = synth.pc_mixture(6000, 50, seed=1)
+    r[100:140] = r[100]                   # 40 identical cells: more ties than candidates for k=15
+    r[7] = r[8]
+    fi, fd, st = core.knn(r, r, 15, "euclidean", drop_first=True, mode="fast", return_stats=True)
+    ei, ed = core.knn(r, r, 15, "euclidean", drop_first=True, mode="exact")
+    assert same_bits(fd, ed) and np.array_equal(fi, ei)
+    oi, od = O.knn(r[:300], r, 15, "euclidean", drop_first=True)
+    assert same_bits(fd[:300], od) and np.array_equal(fi[:300], oi)
+
+
+def test_fast_mask_nan_offset(core):
+    from nabo_b200 import synth
+    q = synth.pc_mixture(700, 30, seed=101)
+    r = synth.pc_mixture(3000, 30, seed=1)
+    q[5, 3] = np.nan
+    r[17, 0] = np.nan
+    mask = np.zeros(3000, bool)
+    mask[::3] = True
+    for kw in (dict(ref_mask=mask), dict(idx_offset=12345), dict(ref_mask=mask, idx_offset=7)):
+        fi, fd = core.knn(q, r, 20, "euclidean", mode="fast", **kw)
+        ei, ed = core.knn(q, r, 20, "euclidean", mode="exact", **kw)
+        assert same_bits(fd, ed) and np.array_equal(fi, ei)
+    off = mask.copy()
+    off[:] = True
+    off[:10] = False                       # only 10 usable references, k = 20 -> masked tail
+    fi, fd = core.knn(q, r, 20, "euclidean", ref_mask=off, mode="fast")
+    ei, ed = core.knn(q, r, 20, "euclidean", ref_mask=off, mode="exact")
+    assert same_bits(fd, ed) and np.array_equal(fi, ei)
+
+
+def test_fast_badly_scaled_inputs(core):
+    """Power-of-two rescaling keeps huge / tiny coordinates inside FP16 range."""
+    from nabo_b200 import synth
+    for scale in (1e-6, 1.0, 3e5):
+        q = synth.pc_mixture(400, 20, seed=101) * scale
+        r = synth.pc_mixture(2500, 20, seed=1) * scale
+        fi, fd, st = core.knn(q, r, 12, "euclidean", mode="fast", return_stats=True)
+        ei, ed = core.knn(q, r, 12, "euclidean", mode="exact")
+        assert same_bits(fd, ed) and np.array_equal(fi, ei)
+        assert st["rows_exact_fallback"] <= 8, (scale, st)
+
+
+def _split16(x):
+    hi = x.astype(np.float16).astype(np.float64)
+    lo = (x - hi).astype(np.float16).astype(np.float64)
+    return hi, lo
+
+
+def test_tc_score_error_bound(core):
+    """The certificate assumes |score_tc - score_fp64| <= 2^-16 (4|q||r| + |r|^2 + |q|^2).
+    Measure it on the threshold candidates of many queries and require a >= 4x margin."""
+    from nabo_b200 import synth
+    worst = 0.0
+    for seed, (n, m, g, k) in enumerate([(6000, 30000, 50, 30), (4000, 9000, 25, 10), (3000, 4000, 52, 60)]):
+        q = synth.pc_mixture(n, g, seed=200 + seed)
+        r = synth.pc_mixture(m, g, seed=300 + seed)
+        c = core.knn_candidates(q, r, k, "euclidean")
+        sc = c["scal"][0]
+        kp = c["cand"].shape[1]
+        fin = np.isfinite(c["tau"]) & (c["cand"][:, kp - 1] >= 0)
+        assert fin.mean() > 0.99
+        qi = np.nonzero(fin)[0]
+        rj = c["cand"][qi, kp - 1]
+        qh, ql = _split16(q[qi] * sc)
+        rh, rl = _split16(r[rj] * sc)
+        rt, qt = rh + rl, qh + ql
+        nn = (rt * rt).sum(1)
+        n1 = nn.astype(np.float16).astype(np.float64)
+        n2 = (nn - n1).astype(np.float16).astype(np.float64)
+        n3 = (nn - n1 - n2).astype(np.float16).astype(np.float64)
+        s64 = (n1 + n2 + n3) - 2.0 * ((qh * rh).sum(1) + (qh * rl).sum(1) + (ql * rh).sum(1))
+        qn, rn = np.sqrt((qt * qt).sum(1)), np.sqrt(nn)
+        np.testing.assert_allclose(c["qn2"][qi], (qt * qt).sum(1), rtol=1e-12)
+        rel = np.abs(c["tau"][qi].astype(np.float64) - s64) / (4 * qn * rn + rn * rn + qn * qn)
+        worst = max(worst, float(rel.max()))
+    print("max tensor-core score error / bound term = %.3e (certificate constant 2^-16 = %.3e)" % (worst, 2.0 ** -16))
+    assert worst < 2.0 ** -18

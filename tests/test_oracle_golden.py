@@ -166,3 +166,25 @@ def test_c1_scale(golden):
     assert O.tie_classes_equal(tidx, tdst, g["tgt_knn"].astype(np.int64), g["tgt_knn_dist"])
     _, w = O.snn_weights(g["tgt_knn"].astype(np.int64), g["ref_knn"].astype(np.int64), k)
     np.testing.assert_allclose(O.mapping_scores(g["tgt_knn"].astype(np.int64), w, n), g["score_default"], rtol=1e-12)
+
+
+def test_c_port_matches_golden_and_numpy(golden):
+    """The plain-C port (timed as the CPU baseline) is bit-identical to the reference kernels."""
+    from oracle import c_port
+    g = golden("kernels")
+    assert bit_equal(c_port.dist(g["x"], g["y"], "euclidean"), g["euclidean"])
+    assert bit_equal(c_port.dist(g["x"], g["y"], "mod_canberra", 0.25), g["canberra_0p25"])
+    m = golden("mapping_ignore")
+    uc, k = int(m["use_comps"]), int(m["k"])
+    ref, tgt = m["ref"][:, :uc], m["tgt"][:, :uc]
+    i1, d1 = c_port.knn(tgt, ref, k, "mod_canberra", float(m["f"]), mask=m["mask"], nthreads=2)
+    i2, d2 = O.knn(tgt, ref, k, "mod_canberra", float(m["f"]), mask=m["mask"])
+    assert np.array_equal(i1, i2) and bit_equal(d1, d2)
+    i1, d1 = c_port.knn(ref, ref, k, "euclidean", drop_first=True)
+    i2, d2 = O.knn(ref, ref, k, "euclidean", drop_first=True)
+    assert np.array_equal(i1, i2) and bit_equal(d1, d2)
+    cnt = c_port.snn_counts(i2.astype(np.int32), i2.astype(np.int32))
+    assert np.array_equal(cnt, O.snn_counts(i2, i2))
+    lut = O.snn_weight_lut(k)
+    np.testing.assert_allclose(c_port.scores(i2, cnt, lut, ref.shape[0]), O.mapping_scores(i2, lut[cnt], ref.shape[0]),
+                               rtol=1e-13)
