@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the nabo cell-projection hot path on B200 (contract: see task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--metric ...]
+
+Workload (BASELINE.json configs[1]): 100 000 target cells mapped onto a 100 000-cell
+reference, 50 PCs, k = 30.  One *step* = one pass of the hot path over one batch of target
+cells: fused distance + per-query top-k (`Mapping.map_target`'s `_calc_dist`), SNN neighbour
+weights (`_calc_snn`) and per-reference mapping scores (`Graph.get_mapping_score`).  The
+reference self-kNN table those weights need (`make_ref_graph`) is built once in setup.
+Headline metric = target cells mapped per second; the Euclidean metric is the headline
+(north_star quotes its targets on it), modified Canberra - the reference's own target->ref
+metric - is measured in the same run and reported under "mod_canberra".
+
+N > 1 (torchrun, one rank per GPU): targets are sharded, the reference is replicated, no
+data-path collective -> weak scaling; value = all ranks' cells / max-over-ranks time.
+
+`--impl reference`: the reference's CPU algorithm (oracle/nabo_oracle.c, a loop-for-loop
+port pinned against the unmodified reference; nabo itself is Python + numba and
+/root/reference does not exist on the GPU box) on all host threads, on a bounded sample of
+the same workload per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--metric", default="euclidean", choices=["euclidean", "mod_canberra", "cosine"])
+    ap.add_argument("--n-ref", type=int, default=100_000)
+    ap.add_argument("--n-query", type=int, default=100_000, help="target cells per GPU per step")
+    ap.add_argument("--comps", type=int, default=50)
+    ap.add_argument("--k", type=int, default=30)
+    ap.add_argument("--engine", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the modified-Canberra measurement")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per cpu_baseline sample")
+    return ap.parse_args()
+
+
+WORKLOAD = "config2: {nq} target x {nr} reference cells, {g} PCs, k={k}, {metric}"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {}
+        for n in dir(nv):
+            if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason"):
+                v = getattr(nv, n)
+                if isinstance(v, int) and v:
+                    names.setdefault(v, n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit and nm not in ("GpuIdle", "None", "All"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        snake = {"SwPowerCap": "sw_power_cap", "HwSlowdown": "hw_slowdown", "HwThermalSlowdown": "hw_thermal_slowdown",
+                 "SwThermalSlowdown": "sw_thermal_slowdown", "HwPowerBrakeSlowdown": "hw_power_brake_slowdown",
+                 "SyncBoost": "sync_boost", "ApplicationsClocksSetting": "applications_clocks_setting",
+                 "DisplayClockSetting": "display_clock_setting"}
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "samples": len(self.samples),
+                "reasons": sorted(snake.get(r, r) for r in self.reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline / reference arm
+def cpu_reference_rate(ref, tgt, ref_knn, k, metric, seconds, threads):
+    """Targets/s of the reference algorithm (C port) on `threads` host threads, on a bounded
+    sample of the workload: distances to every reference cell, full-row sort, SNN counts, scores."""
+    from oracle import c_port, nabo_oracle as O
+    c_port.build()
+    m = "euclidean" if metric == "euclidean" else "mod_canberra"
+    if metric == "cosine":
+        raise SystemExit("the reference has no cosine metric; no CPU baseline for it")
+    t0 = time.perf_counter()
+    c_port.knn(tgt[:4], ref, k, m, 0.25, nthreads=1)
+    per = (time.perf_counter() - t0) / 4
+    n = int(max(threads * 2, min(len(tgt), seconds * threads / max(per, 1e-6))))
+    n = max(threads, n // threads * threads)
+    sample = tgt[:n]
+    lut = O.snn_weight_lut(k)
+    t0 = time.perf_counter()
+    idx, _ = c_port.knn(sample, ref, k, m, 0.25, nthreads=threads)
+    cnt = c_port.snn_counts(idx, ref_knn, nthreads=threads)
+    c_port.scores(idx, cnt, lut, ref.shape[0])
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from nabo_b200 import synth
+    from oracle import c_port
+    threads = os.cpu_count() or 1
+    ref = synth.pc_mixture(a.n_ref, a.comps, seed=1)
+    tgt = synth.pc_mixture(min(a.n_query, 4096 * 4), a.comps, seed=101)
+    # the reference table the SNN step needs: built with the same CPU port on a subset is too slow
+    # at 100k x 100k (hours), so the bounded sample uses random neighbour lists of the right shape;
+    # the SNN/score cost does not depend on their values.
+    rng = np.random.default_rng(0)
+    ref_knn = rng.integers(0, a.n_ref, size=(a.n_ref, a.k), dtype=np.int32)
+    # size each step to ~3 s of wall time
+    rate0, n0, _ = cpu_reference_rate(ref, tgt, ref_knn, a.k, a.metric, 1.0, threads)
+    per_step = int(max(threads, min(len(tgt), rate0 * 3.0)) // threads * threads)
+    times = []
+    for s in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        idx, _ = c_port.knn(tgt[:per_step], ref, a.k, "euclidean" if a.metric == "euclidean" else "mod_canberra",
+                            0.25, nthreads=threads)
+        cnt = c_port.snn_counts(idx, ref_knn, nthreads=threads)
+        c_port.scores(idx, cnt, np.zeros(a.k + 1), a.n_ref)
+        dt = time.perf_counter() - t0
+        if s >= a.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = per_step / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "target_cells_mapped_per_s", "value": value, "unit": "cells/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(nq=a.n_query, nr=a.n_ref, g=a.comps, k=a.k, metric=a.metric),
+                   "sample": "%d target cells per step against all %d reference cells" % (per_step, a.n_ref)},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port",
+                         "sample": "%d targets x %d references per step, %d host threads; C port of "
+                                   "nabo/_mapping.py:16-45,135-146,186-198 + _graph.py:643-653" % (per_step, a.n_ref, threads)},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from nabo_b200 import build, core, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus > 1 and world != a.gpus:
+        raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (a.gpus, a.gpus, world))
+    build.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    g, k, M, N = a.comps, a.k, a.n_ref, a.n_query
+    ref_h = synth.pc_mixture(M, g, seed=1)
+    tgt_h = synth.pc_mixture(N, g, seed=101 + rank)             # this rank's target shard
+    ref = torch.from_numpy(ref_h).to(dev)
+    tgt = torch.from_numpy(tgt_h).to(dev)
+    tgt_pin = torch.from_numpy(tgt_h).pin_memory()
+    # setup (untimed): reference self-kNN = make_ref_graph's sorted rows
+    ref_knn, _ = core.knn(ref, ref, k, "euclidean", drop_first=True, mode=a.engine)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(metric, q, stats=False):
+        r = core.knn(q, ref, k, metric, 0.25, mode=a.engine, return_stats=stats)
+        idx, dst = r[0], r[1]
+        cnt, w = core.snn_weights(idx, ref_knn, k)
+        sc = core.mapping_scores(idx, cnt, M, k)
+        return idx, dst, cnt, w, sc, (r[2] if stats else None)
+
+    def timed(metric, steps, warmup, e2e=False):
+        for _ in range(warmup):
+            if e2e:
+                host_step(metric)
+            else:
+                step(metric, tgt)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kern_ms, launches, fallback = [], 0, 0
+        sampler = ClockSampler(local)
+        sampler.start()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            flush.zero_()                                   # evict L2 between timed iterations (untimed)
+            ev[i][0].record()
+            if e2e:
+                host_step(metric)
+            else:
+                out = step(metric, tgt, stats=True)
+                st = out[5]
+                kern_ms.append(st["main_kernel_ms"])
+                launches += st["kernel_launches"] + 1 + score_launches(M)
+                fallback += st["rows_exact_fallback"]
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop()
+        total_ms = sum(s.elapsed_time(e) for s, e in ev)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"ms_total": float(t.item()), "kern_ms": kern_ms, "launches": launches, "fallback": fallback,
+                "clocks": clocks, "wall_s": wall}
+
+    def score_launches(m):
+        bits = 1
+        while (1 << bits) <= m:
+            bits += 1
+        return 1 + 3 * ((bits + 7) // 8) + 1
+
+    out_pin = {}
+
+    def host_step(metric):
+        """Public host-buffer API: pinned host targets in, pinned host results out."""
+        res = core.map_cells(tgt_pin, ref, ref_knn, k, metric=metric, dist_factor=0.25, mode=a.engine)
+        for name in ("idx", "dist", "weights", "scores"):
+            t = res[name]
+            if name not in out_pin:
+                out_pin[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            out_pin[name].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    main = timed(a.metric, a.steps, a.warmup)
+    e2e = timed(a.metric, max(3, a.steps // 2), 2, e2e=True)
+    ms_step = main["ms_total"] / a.steps
+    value = world * N / (ms_step / 1e3)
+    e2e_steps = max(3, a.steps // 2)
+    e2e_value = world * N / (e2e["ms_total"] / e2e_steps / 1e3)
+    h2d = N * g * 8
+    d2h = N * k * (4 + 8 + 8) + M * 8
+
+    kern = sum(main["kern_ms"]) / max(1, len(main["kern_ms"]))
+    if a.metric in ("euclidean", "cosine") and a.engine == "fast":
+        flops = 2.0 * g * N * M                                   # 2*g flop per pair, true g
+        roof = {"bound": "tensor", "achieved": flops / (kern * 1e-3) / 1e12, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "kernel": "tc::candidates_kernel",
+                "peak_source": "%s bf16 burst (kernel timed per launch)" % peaks["source"],
+                "executed_tflops": flops * (((3 * g + 3 + 15) // 16 * 16) / g) / (kern * 1e-3) / 1e12,
+                "traffic": None}
+    else:
+        ops = 5.0 * g * N * M if a.metric == "mod_canberra" else 3.0 * g * N * M
+        roof = {"bound": "fp64", "achieved": ops / (kern * 1e-3) / 1e12, "peak": 37.0,
+                "unit": "TFLOP/s", "kernel": "knn_exact_kernel",
+                "peak_source": "nominal B200 FP64 (no measured FP64 peak in MEASURED_PEAKS.json)", "traffic": None}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    tr = os.path.join(ROOT, "profiles", "bench_traffic.json")
+    if os.path.exists(tr):
+        roof["traffic"] = json.load(open(tr)).get(roof["kernel"])
+
+    line = {
+        "metric": "target_cells_mapped_per_s", "value": value, "unit": "cells/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 (candidates: f16x2-split tcgen05, f32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(nq=N, nr=M, g=g, k=k, metric=a.metric), "engine": a.engine,
+                   "per_gpu_targets": N, "sharding": "targets (reference replicated, no collective)",
+                   "l2": "512 MB buffer rewritten between timed iterations", "inputs_resident": True},
+        "clocks": {"sm_mhz": main["clocks"]["sm_mhz"], "sm_max_mhz": main["clocks"]["sm_max_mhz"],
+                   "reasons": main["clocks"]["reasons"], "samples": main["clocks"]["samples"]},
+        "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e["ms_total"] / e2e_steps, "api": "nabo_b200.core.map_cells (pinned host in/out)"},
+        "gpu_launches": main["launches"],
+        "roofline": roof,
+        "kernel_ms_per_step": kern,
+        "rows_exact_fallback_per_step": main["fallback"] / a.steps,
+    }
+
+    if rank == 0 and world == 1 and not a.no_secondary and a.metric == "euclidean":
+        sec_steps = max(2, a.steps // 5)
+        sec = timed("mod_canberra", sec_steps, 1)
+        sk = sum(sec["kern_ms"]) / len(sec["kern_ms"])
+        line["mod_canberra"] = {
+            "value": N / (sec["ms_total"] / sec_steps / 1e3), "unit": "cells/s", "ms_per_step": sec["ms_total"] / sec_steps,
+            "roofline": {"bound": "fp64", "kernel": "knn_exact_kernel<mod_canberra>",
+                         "achieved": 5.0 * g * N * M / (sk * 1e-3) / 1e12, "unit": "TFLOP/s (5 FP ops per pair-dim)",
+                         "peak": 37.0, "frac": 5.0 * g * N * M / (sk * 1e-3) / 1e12 / 37.0,
+                         "peak_source": "nominal B200 FP64"}}
+
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.metric != "cosine":
+        threads = os.cpu_count() or 1
+        rate, n, dt = cpu_reference_rate(ref_h, tgt_h, ref_knn.cpu().numpy(), k, a.metric, a.cpu_seconds, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": "cells/s", "cores": threads, "kind": "port",
+                                "sample": "%d of the %d target cells against all %d reference cells in %.1f s "
+                                          "(C port of the reference loops, %d host threads)" % (n, N, M, dt, threads)}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
