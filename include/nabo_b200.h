@@ -151,6 +151,10 @@ int nabo_classify_targets(const int32_t* tgt_knn, const uint8_t* counts, const d
  * CSR form: indptr int64 (n_cells+1), col int32, val float32 over ALL genes of
  * the dataset; gene_pos[n_genes_total] = position in the model's gene order or -1.
  * components (n_comps x G) row-major, mean (G).  out (n_cells x ldo) FP64. */
+/* z alone (n_cells x G, FP64), bit-identical to get_scaled_values (nabo/_dataset.py:912). */
+int nabo_scale_dense(const float* counts, int ld, int n_cells, const int32_t* gene_idx, int G,
+                     const float* sf, const double* mu, const double* sigma, double* out, int ldo,
+                     void* stream);
 int nabo_project_dense(const float* counts, int ld, int n_cells, const int32_t* gene_idx, int G,
                        const float* sf, const double* mu, const double* sigma,
                        const double* components, const double* mean, int n_comps, double* out,

@@ -19,7 +19,7 @@ from ._lib import METRICS, MODE_EXACT, MODE_FAST, check, lib, require_device
 
 __all__ = ["euclidean_dist", "mod_canberra_dist", "cosine_dist", "knn", "knn_candidates", "rerank_exact", "merge_topk",
            "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets",
-           "project", "project_csr", "map_cells", "resolve_metric"]
+           "project", "project_csr", "scale_counts", "map_cells", "resolve_metric"]
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -330,6 +330,22 @@ def project(counts, gene_idx, sf, mu, sigma, components, mean):
     out = torch.empty((n, nc), dtype=torch.float64, device=cd.device)
     check(lib().nabo_project_dense(_ptr(cd), ld, n, _ptr(gi), G, _ptr(sfd), _ptr(mud), _ptr(sgd), _ptr(cm),
                                    _ptr(mn), nc, _ptr(out), nc, C.c_void_p(_stream())), "project_dense")
+    return _out(out, host)
+
+
+def scale_counts(counts, gene_idx, sf, mu, sigma):
+    """``get_scaled_values`` core (nabo/_dataset.py:905-913) on a dense count block -> z (cells x G) float64."""
+    require_device()
+    host = _is_host(counts)
+    cd = _dev(counts, torch.float32)
+    gi = _dev(gene_idx, torch.int32)
+    sfd = _dev(sf, torch.float32)
+    mud, sgd = _dev(mu, torch.float64), _dev(sigma, torch.float64)
+    n, ld = cd.shape
+    G = gi.numel()
+    out = torch.empty((n, G), dtype=torch.float64, device=cd.device)
+    check(lib().nabo_scale_dense(_ptr(cd), ld, n, _ptr(gi), G, _ptr(sfd), _ptr(mud), _ptr(sgd), _ptr(out), G,
+                                 C.c_void_p(_stream())), "scale_dense")
     return _out(out, host)
 
 

@@ -99,6 +99,32 @@ extern "C" int nabo_project_dense(const float* counts, int ld, int n_cells, cons
     return 0;
 }
 
+// ------------------------------------------------------------------ scaling alone (get_scaled_values)
+__global__ void __launch_bounds__(256)
+scale_dense_kernel(const float* __restrict__ counts, int ld, int n_cells, const int32_t* __restrict__ gene_idx,
+                   int G, const float* __restrict__ sf, const double* __restrict__ mu,
+                   const double* __restrict__ sigma, double* __restrict__ out, int ldo) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n_cells * G) return;
+    const int cell = (int)(e / G), g = (int)(e - (long long)cell * G);
+    const int col = gene_idx[g];
+    const float a = col >= 0 ? counts[(long long)cell * ld + col] : 0.0f;
+    out[(long long)cell * ldo + g] = scaled_value(a, sf[cell], mu[g], sigma[g]);
+}
+
+extern "C" int nabo_scale_dense(const float* counts, int ld, int n_cells, const int32_t* gene_idx, int G,
+                                const float* sf, const double* mu, const double* sigma, double* out, int ldo,
+                                void* stream) {
+    NABO_ARG(n_cells >= 0 && G >= 1 && ldo >= G, "scale: bad sizes");
+    if (n_cells == 0) return 0;
+    NABO_ARG(counts && gene_idx && sf && mu && sigma && out, "scale: null pointer");
+    const long long tot = (long long)n_cells * G;
+    scale_dense_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(counts, ld, n_cells, gene_idx, G,
+                                                                                     sf, mu, sigma, out, ldo);
+    NABO_LAUNCH_CHECK("scale_dense_kernel");
+    return 0;
+}
+
 // ------------------------------------------------------------------ CSR form
 // workspace: ct [G][nc] (components transposed), z0 [G], p0 [nc]
 __global__ void __launch_bounds__(256)

@@ -1,0 +1,318 @@
+"""``Graph``: the part of ``nabo.Graph`` (nabo/_graph.py) that sits on the hot path.
+
+Kept verbatim: ``Graph()`` (an ``nx.Graph``), ``load_from_h5(fn, name, kind)``,
+``get_mapping_score(target, ...)`` with every keyword, ``classify_target`` and the attributes
+``refName, refNodes, refG, targetNames, targetNodes``.  The per-reference score and the
+per-target cluster vote run on the GPU from the columnar graph arrays (``knn``, ``snn``)
+that ``Mapping.calc_snn`` stores; the networkx structure is still populated so that
+downstream networkx code keeps working (``materialize=False`` skips that for large graphs).
+The rest of ``nabo.Graph`` (layouts, clustering, GML, DE helpers; nabo/_graph.py:118-554,
+794-1055) is downstream analytics on the result and is out of scope.
+"""
+from __future__ import annotations
+
+import os
+from collections import Counter
+from typing import Dict, List, Optional
+
+import networkx as nx
+import numpy as np
+
+from . import core
+from .store import Group, open_file
+
+__all__ = ["Graph"]
+
+
+class _Sample:
+    """Columnar arrays of one loaded sample."""
+
+    def __init__(self, nodes: List[str], knn: np.ndarray, snn: np.ndarray, k: int):
+        self.nodes, self.knn, self.snn, self.k = nodes, knn, snn, k
+        self.index = {n: i for i, n in enumerate(nodes)}
+
+
+class Graph(nx.Graph):
+    """Nabo's SNN graph (inherits networkx's ``Graph``)."""
+
+    def __init__(self):
+        super().__init__()
+        self.refName = None
+        self.refNodes: List[str] = []
+        self.refG = None
+        self.targetNames: List[str] = []
+        self.targetNodes: Dict[str, List[str]] = {}
+        self.deTestCells: List[str] = None
+        self.deCtrlCells: List[str] = None
+        self.clusters: Dict[str, str] = {}
+        self._samples: Dict[str, _Sample] = {}
+        self._refIndex: Dict[str, int] = {}
+
+    # ------------------------------------------------------------------ loading
+    def load_from_h5(self, fn: str, name: str, kind: str, materialize: Optional[bool] = None) -> None:
+        """nabo/_graph.py:31-116.  Reads the columnar ``<uid>_graph`` group written by
+        ``nabo_b200.Mapping`` or the reference's one-dataset-per-node layout."""
+        if os.path.exists(fn) is False:
+            raise IOError("ERROR: File %s does not exist" % fn)
+        if kind == "reference":
+            if self.refName is not None:
+                raise ValueError("ERROR: A reference kind is already loaded")
+        elif kind == "target":
+            if name in self.targetNames:
+                raise ValueError("ERROR: %s target group already present in graph" % name)
+            if self.refName is None:
+                raise ValueError("ERROR: Please load reference kind first")
+        else:
+            raise ValueError('ERROR: Kind can be either "reference" or "target"')
+        try:
+            h5 = open_file(fn, mode="r")
+        except (IOError, OSError):
+            raise IOError("ERROR: Unable to open file %s" % fn)
+        if kind == "reference":
+            try:
+                saved_name = h5["name_stash/ref_name"][0].decode("UTF-8")
+                uid = h5["name_stash/ref_name"][1].decode("UTF-8")
+            except KeyError:
+                raise KeyError("ERROR: Could not find stashed names in the mapping file. Make sure reference "
+                               "graph has been created in the mapping file")
+            if name != saved_name:
+                raise KeyError("ERROR: The reference is named %s in the mapping file and not %s. Please verify "
+                               "that you are trying to load right reference." % (saved_name, name))
+        else:
+            try:
+                target_names = h5["name_stash/target_names"][:]
+            except KeyError:
+                raise KeyError("ERROR: Could not find stashed names in the mapping file. Make sure reference "
+                               "graph has been created in the mapping file")
+            uid = None
+            for i in target_names:
+                if i[0].decode("UTF-8") == name:
+                    uid = i[1].decode("UTF-8")
+            if uid is None:
+                raise KeyError("ERROR: The target name not could not be found in the mapping file")
+        grp = uid + "_graph"
+        if grp not in h5:
+            h5.close()
+            raise KeyError("ERROR: Group %s not found in HDF5 file %s" % (grp, fn))
+        g = h5[grp]
+        ref_cells = [x.decode("UTF-8") for x in h5["ref_cells/ref_cells"][:]]
+        if "knn" in g and "snn" in g:
+            new_nodes, edges = self._load_columnar(g, name, kind, ref_cells)
+        else:
+            new_nodes, edges = self._load_per_node(g, name, kind, ref_cells)
+        h5.close()
+        existing = set(self.nodes()) if self.number_of_nodes() else set()
+        dup = [n for n in new_nodes if n in existing]
+        for n in dup:
+            print("WARNING: node %s already present in the graph. Will not add." % n)
+        if materialize is None:
+            materialize = len(edges[0]) <= 5_000_000
+        if materialize:
+            attrs = {"kind": kind, "name": name}
+            self.add_nodes_from((n for n in new_nodes if n not in existing), **attrs)
+            a, b, w = edges
+            self.add_weighted_edges_from(zip(a, b, w))
+        if kind == "reference":
+            self.refName = name
+            self.refNodes = [n for n in new_nodes if n not in existing]
+            self._refIndex = {c + "_" + name: i for i, c in enumerate(ref_cells)}
+            self.refG = self.subgraph(self.refNodes)
+        else:
+            self.targetNames.append(name)
+            self.targetNodes[name] = [n for n in new_nodes if n not in existing]
+        return None
+
+    def _load_columnar(self, g: Group, name: str, kind: str, ref_cells: List[str]):
+        nodes = [x.decode("UTF-8") for x in g["nodes"][:]]
+        knn = np.asarray(g["knn"][:], dtype=np.int32)
+        snn = np.asarray(g["snn"][:], dtype=np.uint8)
+        k = int(g["k"][0])
+        ref_suffix = g["ref_suffix"][0].decode("UTF-8") if "ref_suffix" in g else (self.refName or name)
+        self._samples[name] = _Sample(nodes, knn, snn, k)
+        lut = core.snn_weight_lut(k)
+        rows, cols = np.nonzero(snn > 0)
+        nb = knn[rows, cols]
+        w = lut[snn[rows, cols]]
+        if kind == "reference":
+            # undirected graph: the later add_edge wins (nx.Graph semantics of _calc_snn, :196-198):
+            # targets are processed in row order, so for a pair {a, b} the weight seen from max(a, b) stays
+            hi, lo = np.maximum(rows, nb), np.minimum(rows, nb)
+            from_hi = rows >= nb
+            order = np.lexsort((from_hi, lo, hi))           # per pair: edge seen from `lo` first, from `hi` last
+            hi, lo, w = hi[order], lo[order], w[order]
+            last = np.ones(len(hi), dtype=bool)
+            last[:-1] = (hi[:-1] != hi[1:]) | (lo[:-1] != lo[1:])
+            hi, lo, w = hi[last], lo[last], w[last]
+            a = [nodes[i] for i in lo]
+            b = [nodes[i] for i in hi]
+            w = list(w)
+            if "fix_edges" in g:
+                fw = float(g["fix_weight"][0])
+                for x, y in np.asarray(g["fix_edges"][:]):
+                    a.append(nodes[int(x)])
+                    b.append(nodes[int(y)])
+                    w.append(fw)
+            return nodes, (a, b, w)
+        ref_names = [c + "_" + ref_suffix for c in ref_cells]
+        a = [nodes[i] for i in rows]
+        b = [ref_names[j] for j in nb]
+        return nodes, (a, b, list(w))
+
+    def _load_per_node(self, g: Group, name: str, kind: str, ref_cells: List[str]):
+        """Reference layout: dataset per node = rows of [neighbour name, str(weight)] (nabo/_mapping.py:265-270)."""
+        nodes = [n for n in g]
+        a, b, w = [], [], []
+        for node in nodes:
+            for j in g[node]:
+                a.append(node)
+                b.append(j[0].decode("UTF-8"))
+                w.append(float(j[1].decode("UTF-8")))
+        if kind == "target":
+            ref_name = self.refName
+            ridx = {c + "_" + ref_name: i for i, c in enumerate(ref_cells)}
+            kmax = max(Counter(a).values()) if a else 1
+            knn = np.full((len(nodes), kmax), -1, dtype=np.int32)
+            wts = np.zeros((len(nodes), kmax), dtype=np.float64)
+            pos = {n: i for i, n in enumerate(nodes)}
+            fill = np.zeros(len(nodes), dtype=np.int64)
+            for x, y, ww in zip(a, b, w):
+                i = pos[x]
+                knn[i, fill[i]] = ridx[y]
+                wts[i, fill[i]] = ww
+                fill[i] += 1
+            s = _Sample(nodes, knn, None, kmax)
+            s.weights = wts
+            self._samples[name] = s
+        return nodes, (a, b, w)
+
+    # ------------------------------------------------------------------ mapping score
+    def get_mapping_score(self, target: str, min_weight: float = 0, min_score: float = 0, weighted: bool = True,
+                          by_cluster: bool = False, sorted_names_only: bool = False, top_n_only: int = None,
+                          all_nodes: bool = True, score_multiplier: int = 1000, ignore_nodes: List[str] = None,
+                          include_nodes: List[str] = None, remove_suffix: bool = False, verbose: bool = False):
+        """nabo/_graph.py:555-697; the per-reference accumulation (:643-653) runs on the GPU."""
+        if by_cluster:
+            if not self.clusters:
+                raise ValueError('ERROR: Calculate clusters first using "make_clusters" or import clusters using '
+                                 '"import_clusters"')
+        if target not in self.targetNames:
+            raise ValueError("ERROR: %s not present in graph" % target)
+        if ignore_nodes is not None and include_nodes is not None:
+            raise ValueError("ERROR: PLease provide only one of either 'ignore_nodes' or 'include_nodes' at a time")
+        s = self._samples[target]
+        tset = s.index
+        ignore = [] if ignore_nodes is None else [n for n in ignore_nodes if n in tset]
+        include = list(self.targetNodes[target]) if include_nodes is None else [n for n in include_nodes if n in tset]
+        include = list(set(include).difference(ignore))
+        if len(include) == 0:
+            raise ZeroDivisionError("division by zero")          # len(include_nodes) == 0 upstream (:652)
+        mask = np.zeros(len(s.nodes), dtype=np.uint8)
+        mask[[tset[n] for n in include]] = 1
+        m = len(self._refIndex)
+        if s.snn is not None:
+            vals = core.mapping_scores(s.knn, s.snn, m, s.k, include=mask, min_weight=float(min_weight),
+                                       min_score=-np.inf, weighted=bool(weighted),
+                                       score_multiplier=float(score_multiplier))
+        else:                                                    # graph loaded from the per-node layout
+            vals = _scores_from_weights(s.knn, s.weights, m, mask, min_weight, weighted, score_multiplier)
+        if verbose:
+            deg = np.zeros(m, dtype=np.int64)
+            valid = (s.knn >= 0) & ((s.snn > 0) if s.snn is not None else (s.weights > 0)) & (mask[:, None] > 0)
+            np.add.at(deg, s.knn[valid], 1)
+            print("INFO: The bipartite graph has %d edges" % int(valid.sum()))
+            print("INFO: Mapping calculated against %d %s nodes" % (len(include), target))
+            print("INFO: %d reference nodes do not connect with any target node" % int((deg == 0).sum()))
+            print("INFO: %d target nodes do not connect with any reference node"
+                  % int((~valid.any(axis=1) & (mask > 0)).sum()))
+        score = {n: float(vals[self._refIndex[n]]) for n in self.refNodes}
+
+        if by_cluster:
+            cluster_dict = self.clusters
+            cluster_values = {x: [] for x in set(cluster_dict.values())}
+            na_cluster_score = []
+            for node in score:
+                try:
+                    cluster_values[cluster_dict[node]].append(score[node])
+                except KeyError:
+                    na_cluster_score.append(score[node])
+            if len(na_cluster_score) > 0:
+                if "NA" not in cluster_values:
+                    cluster_values["NA"] = []
+                else:
+                    print("WARNING: 'NA' cluster already exists. Appending value to it")
+                cluster_values["NA"].extend(na_cluster_score)
+            return cluster_values
+        if sorted_names_only:
+            if top_n_only is not None:
+                if top_n_only > len(score):
+                    raise ValueError("ERROR: Value of top_n_only should be less than total number of nodes in "
+                                     "reference graph")
+                retval = [x[0] for x in sorted(score.items(), key=lambda x: x[1])][::-1][:top_n_only]
+            else:
+                ms = {k: v for k, v in score.items() if v >= min_score}
+                retval = [x[0] for x in sorted(ms.items(), key=lambda x: x[1])][::-1]
+            return [x.rsplit("_", 1)[0] for x in retval] if remove_suffix else retval
+        if not all_nodes:
+            retval = {k: v for k, v in score.items() if v >= min_score}
+        else:
+            retval = {k: v if v >= min_score else 0 for k, v in score.items()}
+        return [x.rsplit("_", 1)[0] for x in retval] if remove_suffix else retval
+
+    # ------------------------------------------------------------------ classification
+    def import_clusters(self, cluster_dict: Dict[str, str]) -> None:
+        """Attach reference cluster labels (node name -> label), cf. nabo/_graph.py:398-432."""
+        self.clusters = {k: v for k, v in cluster_dict.items() if k in self._refIndex}
+
+    def classify_target(self, target: str, weight_frac: float = 0.5, min_degree: int = 2, min_weight: float = 0.1,
+                        cluster_dict: Dict[str, int] = None, na_label: str = "NA", ret_counts: bool = False) -> dict:
+        """nabo/_graph.py:722-792 on the GPU (per-target cluster vote)."""
+        if cluster_dict is None:
+            if not self.clusters:
+                raise ValueError("ERROR: Please make sure that clusters are set for each reference node")
+            cluster_dict = self.clusters
+        s = self._samples[target]
+        if s.snn is None:
+            raise ValueError("ERROR: classify_target needs a graph stored in the columnar layout")
+        labels = sorted(set(cluster_dict.values()), key=str)
+        lid = {l: i for i, l in enumerate(labels)}
+        ref_labels = np.full(len(self._refIndex), -1, dtype=np.int32)
+        for node, lab in cluster_dict.items():
+            if node in self._refIndex:
+                ref_labels[self._refIndex[node]] = lid[lab]
+        out = core.classify_targets(s.knn, s.snn, ref_labels, len(labels), s.k, weight_frac=weight_frac,
+                                    min_degree=min_degree, min_weight=min_weight)
+        classified = [labels[i] if i >= 0 else na_label for i in out]
+        if ret_counts:
+            counts = Counter(classified)
+            if na_label not in counts:
+                counts[na_label] = 0
+            for i in set(cluster_dict.values()):
+                if i not in counts:
+                    counts[i] = 0
+            return counts
+        return dict(zip(s.nodes, classified))
+
+
+def _scores_from_weights(knn, weights, n_ref, mask, min_weight, weighted, mult):
+    """Per-node-layout graphs carry weights, not SNN counts: map weight -> rank table -> GPU kernel."""
+    vals = np.unique(weights[weights > 0])
+    lut = np.concatenate([[0.0], vals])
+    if len(lut) > 255:
+        raise ValueError("ERROR: more than 254 distinct edge weights; store the graph in the columnar layout")
+    cnt = np.searchsorted(vals, weights).astype(np.uint8) + 1
+    cnt[weights <= 0] = 0
+    import torch
+    from . import _lib
+    import ctypes as C
+    core.require_device()
+    td, cd = core._dev(knn, torch.int32), core._dev(cnt, torch.uint8)
+    ld, md = core._dev(lut, torch.float64), core._dev(mask, torch.uint8)
+    n, kk = td.shape
+    out = torch.empty(n_ref, dtype=torch.float64, device=td.device)
+    L = _lib.lib()
+    ws = torch.empty(int(L.nabo_scores_workspace_bytes(n, kk, n_ref)), dtype=torch.uint8, device=td.device)
+    _lib.check(L.nabo_mapping_scores(core._ptr(td), core._ptr(cd), core._ptr(ld), n, kk, int(n_ref), core._ptr(md),
+                                     int(mask.sum()), float(min_weight), 1 if weighted else 0, float(mult),
+                                     float("-inf"), core._ptr(out), core._ptr(ws), ws.numel(),
+                                     C.c_void_p(core._stream())), "mapping_scores")
+    return out.cpu().numpy()

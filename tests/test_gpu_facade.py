@@ -1,0 +1,169 @@
+"""Drop-in surface (Dataset / Mapping / Graph) end to end on the GPU against the golden
+outputs of the unmodified reference."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import nabo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    from nabo_b200 import build
+    build.build()
+
+
+def _write_pca(fn, names, mat, per_cell=False):
+    from nabo_b200 import store
+    h = store.File(fn, "w")
+    if per_cell:                                   # the reference's layout: one dataset per cell
+        g = h.create_group("data")
+        for n, v in zip(names, mat):
+            g.create_dataset(n, data=np.array(v))
+    else:
+        h.create_row_group("data", names, mat)
+    h.close()
+
+
+@pytest.mark.parametrize("name,per_cell", [("mapping_small", False), ("mapping_ignore", True)])
+def test_mapping_graph_end_to_end(tmp_path, golden, name, per_cell):
+    from nabo_b200 import Mapping, Graph, store, synth
+    g = golden(name)
+    uc, k, f = int(g["use_comps"]), int(g["k"]), float(g["f"])
+    ref, tgt = g["ref"], g["tgt"]
+    rn, tn = synth.cell_names(len(ref), "R"), synth.cell_names(len(tgt), "T")
+    ref_fn, tgt_fn, map_fn = (str(tmp_path / x) for x in ("ref.h5", "tgt.h5", "map.h5"))
+    perm = np.random.default_rng(0).permutation(len(ref))          # insertion order must not matter
+    _write_pca(ref_fn, [rn[i] for i in perm], ref[perm], per_cell)
+    _write_pca(tgt_fn, tn, tgt, per_cell)
+    ignore = [rn[i] for i in np.nonzero(g["mask"])[0]] if "mask" in g.files else None
+    random.seed(5)
+    m = Mapping(map_fn, "REF", ref_fn, "data", overwrite=True)
+    assert m.refCells == rn
+    m.set_parameters(uc, k, f, 64)
+    m.make_ref_graph()
+    m.map_target("TGT", tgt_fn, "data", ignore_ref_cells=ignore)
+    with pytest.raises(ValueError, match="target name exists"):
+        m.map_target("TGT", tgt_fn, "data")
+
+    h5 = store.File(map_fn, "r")
+    assert h5["name_stash/ref_name"][0] == b"REF"
+    ruid = h5["name_stash/ref_name"][1].decode()
+    tuid = [i[1].decode() for i in h5["name_stash/target_names"] if i[0] == b"TGT"][0]
+    assert len(ruid) == 30 and [x.decode() for x in h5["ref_cells/ref_cells"][:]] == rn
+    # <uid>_sortedDist/<cell>[:k] and <uid>_dist/<cell> read like the reference's groups
+    rk = np.array([h5[ruid + "_sortedDist"][c][:k] for c in rn])
+    rd = np.array([h5[ruid + "_dist"][c][:k] for c in rn])
+    tk = np.array([h5[tuid + "_sortedDist"][c][:k] for c in tn])
+    td = np.array([h5[tuid + "_dist"][c][:k] for c in tn])
+    assert rk.dtype == np.int64 and td.dtype == np.float64
+    h5.close()
+    gr = g["ref_sorted_full"][:, :k].astype(np.int64)
+    gt = g["tgt_sorted_full"][:, :k].astype(np.int64)
+    assert O.tie_classes_equal(rk, rd, gr, np.take_along_axis(g["ref_dist_full"], gr, 1), head_truncated=True)
+    assert O.tie_classes_equal(tk, td, gt, np.take_along_axis(g["tgt_dist_full"], gt, 1))
+
+    gph = Graph()
+    gph.load_from_h5(map_fn, "REF", "reference")
+    gph.load_from_h5(map_fn, "TGT", "target")
+    assert gph.refName == "REF" and gph.targetNames == ["TGT"]
+    assert gph.refNodes == [c + "_REF" for c in rn] and gph.targetNodes["TGT"] == [c + "_TGT" for c in tn]
+    assert gph.refG.number_of_nodes() == len(rn)
+    # target edges + weights
+    exp = {(tn[int(t)] + "_TGT", rn[int(r)] + "_REF"): float(w)
+           for t, r, w in zip(g["tgt_edge_t"], g["tgt_edge_r"], g["tgt_edge_w"])}
+    got = {(a, b): d["weight"] for a, b, d in gph.edges(data=True) if a.endswith("_TGT") or b.endswith("_TGT")}
+    got = {(a, b) if a.endswith("_TGT") else (b, a): w for (a, b), w in got.items()}
+    same_lists = np.array_equal(np.sort(tk, 1), np.sort(gt, 1)) and np.array_equal(np.sort(rk, 1), np.sort(gr, 1))
+    if same_lists:
+        assert got == exp
+    # reference graph: SNN edges + repair edges
+    exp_ref = {frozenset((rn[int(a)], rn[int(b)])): float(w)
+               for a, b, w in zip(g["ref_edge_a"], g["ref_edge_b"], g["ref_edge_w"])}
+    got_ref = {frozenset((a[:-4], b[:-4])): d["weight"] for a, b, d in gph.refG.edges(data=True)}
+    if same_lists:
+        assert set(got_ref) == set(exp_ref)
+        assert got_ref == exp_ref
+    import networkx as nx
+    assert nx.is_connected(gph.refG)
+    # scores
+    for key, kw in (("score_default", {}), ("score_minw", dict(min_weight=0.12)),
+                    ("score_unweighted", dict(weighted=False)), ("score_minscore", dict(min_score=2.0))):
+        sc = gph.get_mapping_score("TGT", **kw)
+        arr = np.array([sc[c + "_REF"] for c in rn])
+        if same_lists:
+            np.testing.assert_allclose(arr, g[key], rtol=1e-12, atol=0)
+    # variants of the call surface
+    top = gph.get_mapping_score("TGT", sorted_names_only=True, top_n_only=5, remove_suffix=True)
+    assert len(top) == 5 and all(t in rn for t in top)
+    some = [tn[i] + "_TGT" for i in range(0, len(tn), 3)]
+    sub = gph.get_mapping_score("TGT", include_nodes=some)
+    oidx = np.array([i for i in range(0, len(tn), 3)])
+    cnt, w = O.snn_weights(tk, rk, k)
+    np.testing.assert_allclose(np.array([sub[c + "_REF"] for c in rn]),
+                               O.mapping_scores(tk, w, len(rn), include=oidx), rtol=1e-12)
+    nz = gph.get_mapping_score("TGT", all_nodes=False, min_score=1.0)
+    assert all(v >= 1.0 for v in nz.values())
+    with pytest.raises(ValueError):
+        gph.get_mapping_score("TGT", ignore_nodes=some, include_nodes=some)
+    # use_stored_distances: graph rebuilt from the stored rows is identical
+    m2 = Mapping(map_fn, "REF", ref_fn, "data")
+    m2.set_parameters(uc, k, f, 64)
+    m2.map_target("TGT", tgt_fn, "data", use_stored_distances=True)
+    g2 = Graph()
+    g2.load_from_h5(map_fn, "REF", "reference")
+    g2.load_from_h5(map_fn, "TGT", "target")
+    assert g2.get_mapping_score("TGT") == gph.get_mapping_score("TGT")
+    # classification against the oracle
+    labels = {c + "_REF": str(i % 4) for i, c in enumerate(rn)}
+    gph.import_clusters(labels)
+    cls = gph.classify_target("TGT", min_weight=0.05)
+    lab_arr = np.array([i % 4 for i in range(len(rn))])
+    oc = O.classify_targets(tk, w, lab_arr, 4, weight_frac=0.5, min_degree=2, min_weight=0.05)
+    assert [cls[c + "_TGT"] for c in tn] == [str(x) if x >= 0 else "NA" for x in oc]
+
+
+def test_dataset_projection_pipeline(tmp_path, golden):
+    from nabo_b200 import Dataset, store
+    from nabo_b200.dataset import write_dataset
+    g = golden("dataset_small")
+    genes = ["G%04d" % i for i in range(g["counts_ref"].shape[1])]
+    rn = ["R%04d" % i for i in range(g["counts_ref"].shape[0])]
+    tn = ["T%04d" % i for i in range(g["counts_tgt"].shape[0])]
+    rfn, tfn = str(tmp_path / "r.h5"), str(tmp_path / "t.h5")
+    write_dataset(rfn, g["counts_ref"].astype(np.int64), rn, genes)
+    write_dataset(tfn, g["counts_tgt"].astype(np.int64), tn, genes)
+    dr, dt = Dataset(rfn, force_recalc=True), Dataset(tfn, force_recalc=True)
+    for d in (dr, dt):
+        d.set_sf()
+        d.set_gene_stats()
+    hvg = [genes[i] for i in g["gene_idx"]]
+    sp = dr.get_scaling_params(hvg)
+    # scaled values (GPU) are bit-identical to the reference's generator output
+    z = np.array([a for _, a in dt.get_scaled_values(sp, disable_tqdm=True)])
+    assert np.array_equal(z, g["scaled_tgt"])
+    # the PCA fit is host scikit-learn on those values with the reference's batch schedule
+    dr.fit_ipca(hvg, n_comps=20, disable_tqdm=True)
+    assert dr.ipca.genes == hvg
+    np.testing.assert_allclose(dr.ipca.components_, g["components"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(dr.ipca.mean_, g["mean"], rtol=0, atol=1e-12)
+
+    class Model:                                    # the golden model, so projection parity is isolated
+        components_, mean_ = g["components"], g["mean"]
+    for d, names, exp, fn in ((dr, rn, g["pca_ref"], "pr.h5"), (dt, tn, g["pca_tgt"], "pt.h5")):
+        out = str(tmp_path / fn)
+        d.transform_pca(out, "data", Model, sp, disable_tqdm=True)
+        h = store.File(out, "r")
+        got = np.array([h["data"][c][:] for c in names])
+        h.close()
+        np.testing.assert_allclose(got, exp, rtol=0, atol=1e-11 * np.abs(exp).max())
+    with pytest.raises(ValueError):
+        dt.transform_pca(str(tmp_path / "x.h5"), "data", None, sp)
+    with pytest.raises(KeyError):
+        sp2 = sp.rename(index={hvg[0]: "NOT_A_GENE"})
+        dt.transform_pca(str(tmp_path / "x.h5"), "data", Model, sp2)
+    dt.transform_pca(str(tmp_path / "y.h5"), "data", Model, sp2, fill_missing=True)   # missing gene -> value 0

@@ -1,0 +1,134 @@
+"""Host-only tests: the h5py-like store and the facade's argument validation / error behaviour
+(everything the reference checks before it computes, nabo/_mapping.py:296-311, 495-524, 581-612)."""
+import os
+
+import numpy as np
+import pytest
+
+from nabo_b200 import store
+
+
+def test_store_roundtrip(tmp_path):
+    fn = str(tmp_path / "a.h5")
+    h = store.File(fn, "w")
+    g = h.create_group("grp")
+    g.create_dataset("b", data=np.arange(5))
+    g.create_dataset("a", data=[b"x", b"yy"])
+    h.create_dataset("deep/er/ds", shape=(3,), dtype=np.float64)
+    h.create_row_group("rows", ["c2", "c1", "c3"], np.arange(12).reshape(3, 4))
+    dt = np.dtype([("idx", np.uint32), ("val", np.int64)])
+    s = np.zeros(2, dtype=dt)
+    s["idx"], s["val"] = [1, 4], [7, 9]
+    h.create_dataset("cell_data/C1", data=s)
+    h.close()
+    assert os.path.getsize(fn) > 0
+    h = store.File(fn, "r")
+    assert list(h["grp"]) == ["a", "b"]                      # name-sorted iteration, as HDF5
+    assert h["grp/a"][1] == b"yy" and h["grp"]["b"][:].tolist() == [0, 1, 2, 3, 4]
+    assert "deep/er/ds" in h and "deep/xx" not in h and h["deep/er/ds"].shape == (3,)
+    assert list(h["rows"]) == ["c1", "c2", "c3"]
+    assert h["rows"]["c1"][:2].tolist() == [4, 5] and h["rows/c3"][:].tolist() == [8, 9, 10, 11]
+    assert h["cell_data"]["C1"]["idx"].tolist() == [1, 4]
+    with pytest.raises(KeyError):
+        h["nope"]
+    h.close()
+    h = store.File(fn, "a")
+    del h["grp"]
+    h["deep/er/ds"][[0, 2]] = [1.5, 2.5]
+    h.close()
+    h = store.File(fn, "r")
+    assert "grp" not in h and h["deep/er/ds"][:].tolist() == [1.5, 0.0, 2.5]
+    h.close()
+    with pytest.raises(OSError):
+        store.File(str(tmp_path / "missing.h5"), "r")
+
+
+def _pca_file(fn, names, mat):
+    h = store.File(fn, "w")
+    h.create_row_group("data", names, mat)
+    h.close()
+
+
+def test_mapping_validation(tmp_path):
+    from nabo_b200.mapping import Mapping
+    ref_fn, map_fn = str(tmp_path / "ref.h5"), str(tmp_path / "map.h5")
+    names = ["R%03d" % i for i in range(20)]
+    _pca_file(ref_fn, names[::-1], np.random.default_rng(0).normal(size=(20, 6)))
+    with pytest.raises(ValueError, match="Underscores"):
+        Mapping(map_fn, "a__b", ref_fn, "data")
+    with pytest.raises(ValueError, match="cannot be same"):
+        Mapping(ref_fn, "REF", ref_fn, "data")
+    with pytest.raises(ValueError, match="doesn't exist"):
+        Mapping(map_fn, "REF", str(tmp_path / "none.h5"), "data")
+    with pytest.raises(ValueError, match="does not exist"):
+        Mapping(map_fn, "REF", ref_fn, "nogroup")
+    m = Mapping(map_fn, "REF", ref_fn, "data", overwrite=True)
+    assert m.refName == "REF" and m.refCells == names          # bytewise name order, not insertion order
+    with pytest.raises(ValueError, match="set the parameters"):
+        m.calc_dist(ref_fn, "data", "d", "s", [])
+    with pytest.raises(ValueError, match="Set parameters"):
+        m.calc_snn("x", "REF", "g")
+    for bad in (0, -1.0, "abc"):
+        with pytest.raises(ValueError, match="dist_factor"):
+            m.set_parameters(5, 3, bad, 100)
+    m.set_parameters(5, 3, 0.25, 100)
+    with pytest.raises(ValueError, match="same as that of reference"):
+        m.map_target("T", ref_fn, "data")
+    with pytest.raises(ValueError, match="cannot be same"):
+        m.map_target("T", map_fn, "data")
+    with pytest.raises(ValueError, match="same as reference name"):
+        m.map_target("REF", str(tmp_path / "t.h5"), "data")
+    with pytest.raises(ValueError, match="Underscores"):
+        m.map_target("T__1", str(tmp_path / "t.h5"), "data")
+    with pytest.raises(KeyError):
+        m.calc_snn("missing_sortedDist", "T", "g")
+    # re-attach: same ref name OK, different one refused, changed cell set refused
+    m2 = Mapping(map_fn, "REF", ref_fn, "data")
+    assert m2._nameStash["REF"] == m._nameStash["REF"]
+    with pytest.raises(ValueError, match="different ref_name"):
+        Mapping(map_fn, "OTHER", ref_fn, "data")
+    other = str(tmp_path / "ref2.h5")
+    _pca_file(other, names[:-1] + ["ZZZ"], np.zeros((20, 6)))
+    with pytest.raises(ValueError, match="does not match"):
+        Mapping(map_fn, "REF", other, "data")
+
+
+def test_graph_validation(tmp_path):
+    from nabo_b200.graph import Graph
+    g = Graph()
+    with pytest.raises(IOError):
+        g.load_from_h5(str(tmp_path / "none.h5"), "REF", "reference")
+    fn = str(tmp_path / "m.h5")
+    store.File(fn, "w").close()
+    with pytest.raises(ValueError, match="Kind"):
+        g.load_from_h5(fn, "REF", "bogus")
+    with pytest.raises(ValueError, match="load reference kind first"):
+        g.load_from_h5(fn, "T", "target")
+    with pytest.raises(KeyError, match="stashed names"):
+        g.load_from_h5(fn, "REF", "reference")
+    with pytest.raises(ValueError, match="not present"):
+        g.get_mapping_score("T")
+
+
+def test_dataset_host_stats_match_reference(tmp_path, golden):
+    """set_sf / set_gene_stats / get_scaling_params are host code: bit-identical mu, sigma, sf."""
+    from nabo_b200.dataset import Dataset, write_dataset
+    g = golden("dataset_small")
+    counts = g["counts_ref"].astype(np.int64)
+    genes = ["G%04d" % i for i in range(counts.shape[1])]
+    cells = ["R%04d" % i for i in range(counts.shape[0])]
+    fn = str(tmp_path / "ref.h5")
+    write_dataset(fn, counts, cells, genes)
+    d = Dataset(fn, force_recalc=True)
+    assert d.cells == cells and d.genes == genes
+    d.set_sf()
+    assert np.array_equal(d.sf, g["sf_ref"])
+    d.set_gene_stats()
+    hvg = [genes[i] for i in g["gene_idx"]]
+    sp = d.get_scaling_params(hvg)
+    assert np.array_equal(sp["mu"].values, g["mu"]) and np.array_equal(sp["sigma"].values, g["sigma"])
+    assert np.array_equal(d.geneStats.loc[genes, "m"].values, g["gene_m_ref"])
+    d2 = Dataset(fn)                                           # cached size factors are re-loaded
+    assert np.array_equal(d2.sf, g["sf_ref"])
+    with pytest.raises(ValueError, match="None of the input genes"):
+        d.get_scaling_params(["NOPE"])
