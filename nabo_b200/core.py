@@ -265,8 +265,10 @@ def snn_weights(tgt_knn, ref_knn, k: Optional[int] = None):
 
 # ----------------------------------------------------------------------------- (5) scores
 def mapping_scores(tgt_knn, counts, n_ref: int, k: Optional[int] = None, include=None, min_weight: float = 0.0,
-                   min_score: float = 0.0, weighted: bool = True, score_multiplier: float = 1000.0):
-    """Core of ``Graph.get_mapping_score`` (nabo/_graph.py:643-653, 690-693) in array form."""
+                   min_score: float = 0.0, weighted: bool = True, score_multiplier: float = 1000.0,
+                   n_targets_total: Optional[int] = None):
+    """Core of ``Graph.get_mapping_score`` (nabo/_graph.py:643-653, 690-693) in array form.
+    ``n_targets_total`` overrides the divisor (a rank's partial score in the sharded modes)."""
     require_device()
     host = _is_host(tgt_knn, counts)
     td, cd = _dev(tgt_knn, torch.int32), _dev(counts, torch.uint8)
@@ -274,7 +276,7 @@ def mapping_scores(tgt_knn, counts, n_ref: int, k: Optional[int] = None, include
     k = kk if k is None else k
     lut = _dev(snn_weight_lut(k), torch.float64)
     inc = None
-    n_inc = n
+    n_inc = n if n_targets_total is None else int(n_targets_total)
     if include is not None:
         inc_h = np.asarray(include.cpu() if isinstance(include, torch.Tensor) else include)
         if inc_h.dtype != np.bool_ and inc_h.dtype != np.uint8:
