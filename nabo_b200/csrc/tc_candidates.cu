@@ -46,7 +46,7 @@ struct SmemPlan {
 inline SmemPlan plan_smem(int kp) {
     SmemPlan p;
     size_t a = NQ * tile_bytes(kp);
-    size_t sort = (size_t)(NTHREADS / 32 - EPI_WARP0) * CAP * 8;
+    size_t sort = (size_t)(NTHREADS / 32 - EPI_WARP0) * 256 * 4;     // per-warp histogram
     size_t bars = 512;
     size_t budget = 227 * 1024 - 1024;   // keep 1 KB for alignment slack
     size_t left = budget > a + sort + bars ? budget - a - sort - bars : 0;
@@ -169,7 +169,7 @@ pack_kernel(const double* __restrict__ x, int ld, int n, int g, int kp, const do
 struct Params {
     const __half* qa;       // packed queries  [n_qtiles_padded][TILE*kp]
     const __half* rb;       // packed references [n_rtiles][TILE*kp]
-    int n_query, n_ref, kp, n_items, n_rtiles, stages, kprime, kc_out;
+    int n_query, n_ref, kp, n_items, n_rtiles, stages, kprime, kc_out, soft;
     unsigned long long* cand_buf;   // [gridDim][NQ*TILE][CAP]
     int32_t* cand_idx;      // [n_query][kc_out]
     float* cert_tau;        // [n_query]
@@ -183,31 +183,212 @@ struct Barriers {
     uint32_t tmem_base;
 };
 
+// buffer key = raw float bits of the score (high word) | local reference index (low word);
+// the compaction routines convert to an order-preserving integer when they load a key
 __device__ __forceinline__ unsigned long long make_key(float score, uint32_t col) {
-    return ((unsigned long long)float_to_sortable(score) << 32) | col;
+    return ((unsigned long long)__float_as_uint(score) << 32) | col;
 }
 
-// warp-cooperative: sort lane `src`'s buffer, keep the best kprime; returns new (cnt, tau) for src
-__device__ __forceinline__ void compact_buffer(unsigned long long* gbuf, int n, unsigned long long* stage, int lane,
-                                               int kprime, int& new_cnt, float& new_tau) {
-    __syncwarp();      // the owner's appends (plain global stores) are ordered before our loads
+// ---- warp-cooperative compaction entirely in registers -----------------------------------
+// The 128 keys of one query are spread 4 per lane (element i = u*32 + lane) and sorted by
+// score with a bitonic network: strides >= 32 are register-to-register, smaller strides are
+// shuffles.  Only the score is compared (ties keep an arbitrary member; everything dropped
+// still has score >= the new threshold, which is all the certificate needs).
+__device__ __forceinline__ void cex(uint32_t& s0, uint32_t& p0, uint32_t& s1, uint32_t& p1, bool up) {
+    // after: (s0 <= s1) if up else (s0 >= s1)
+    const bool sw = up ? (s1 < s0) : (s0 < s1);
+    if (sw) { uint32_t t = s0; s0 = s1; s1 = t; t = p0; p0 = p1; p1 = t; }
+}
+
+__device__ __forceinline__ void sort128(uint32_t (&s)[4], uint32_t (&pl)[4], int lane) {
 #pragma unroll
-    for (int u = 0; u < CAP / 32; ++u) {
-        const int i = lane + 32 * u;
-        stage[i] = i < n ? __ldcg(gbuf + i) : ~0ull;     // read through L2: never a stale L1 line
+    for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int du = stride >> 5;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if ((u & du) == 0) {
+                        const bool up = (((u * 32) & size) == 0);      // lane bits never reach `size` >= 64
+                        cex(s[u], pl[u], s[u | du], pl[u | du], up);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = u * 32 + lane;
+                    const uint32_t os = __shfl_xor_sync(0xffffffffu, s[u], stride);
+                    const uint32_t op = __shfl_xor_sync(0xffffffffu, pl[u], stride);
+                    const bool up = ((i & size) == 0);
+                    const bool lower = ((lane & stride) == 0);
+                    const bool take_min = (up == lower);
+                    const bool other = take_min ? (os < s[u]) : (s[u] < os);
+                    if (other) { s[u] = os; pl[u] = op; }
+                }
+            }
+        }
+    }
+}
+
+// Exact compaction (once per query per work item, and as the fallback of compact_select):
+// sort lane `src`'s buffer (n live keys), keep the kprime best at the front of the buffer.
+// Returns the new count and threshold through nc / nt (valid on every lane); s / pl hold the
+// sorted keys afterwards.
+__device__ __noinline__ void compact_sort(unsigned long long* gbuf, int n, int lane, int kprime,
+                                          uint32_t (&s)[4], uint32_t (&pl)[4], int& nc, float& nt) {
+    __syncwarp();            // the owner's appends (plain global stores) are ordered before our loads
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = u * 32 + lane;
+        const unsigned long long kv = i < n ? __ldcg(gbuf + i) : 0ull;     // through L2: never a stale L1 line
+        s[u] = i < n ? float_to_sortable(__uint_as_float((uint32_t)(kv >> 32))) : 0xffffffffu;
+        pl[u] = (uint32_t)kv;
+    }
+    sort128(s, pl, lane);
+    nc = n < kprime ? n : kprime;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = u * 32 + lane;
+        if (i < nc) gbuf[i] = ((unsigned long long)__float_as_uint(sortable_to_float(s[u])) << 32) | pl[u];
+    }
+    // threshold = score of element kprime-1 (only meaningful when n >= kprime)
+    const int e = kprime - 1;
+    uint32_t ts = s[0];
+    if ((e >> 5) == 1) ts = s[1];
+    if ((e >> 5) == 2) ts = s[2];
+    if ((e >> 5) == 3) ts = s[3];
+    ts = __shfl_sync(0xffffffffu, ts, e & 31);
+    nt = n >= kprime ? sortable_to_float(ts) : CUDART_INF_F;
+    __syncwarp();
+}
+
+// Cheap running compaction: one 256-bin histogram pass over the scores of the buffer finds a
+// cut with at least kprime keys at or below it; those keys are kept (a few more than kprime),
+// the rest is dropped, and the new threshold is the largest kept score.  Every dropped key
+// lies in a higher bin, i.e. has a strictly larger score, so the certificate invariant
+// ("everything rejected or dropped has score >= tau") holds without an exact selection.
+// If the cut keeps more than max_keep keys (ties, duplicates) the exact sort takes over.
+// hist: 256 counters of this warp in shared memory.
+__device__ __noinline__ void compact_select(unsigned long long* gbuf, int n, int lane, int kprime, int max_keep,
+                                            uint32_t* hist, int& nc, float& nt) {
+    __syncwarp();
+    float fv[4];
+    uint32_t pl[4];
+    float flo = CUDART_INF_F, fhi = -CUDART_INF_F;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = u * 32 + lane;
+        const unsigned long long kv = i < n ? __ldcg(gbuf + i) : 0ull;
+        fv[u] = __uint_as_float((uint32_t)(kv >> 32));
+        pl[u] = (uint32_t)kv;
+        if (i < n) { flo = fminf(flo, fv[u]); fhi = fmaxf(fhi, fv[u]); }
+    }
+    flo = sortable_to_float(__reduce_min_sync(0xffffffffu, float_to_sortable(flo)));
+    fhi = sortable_to_float(__reduce_max_sync(0xffffffffu, float_to_sortable(fhi)));
+    // zero the histogram (8 bins per lane)
+    reinterpret_cast<uint4*>(hist)[lane * 2] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(hist)[lane * 2 + 1] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    const float range = fhi - flo;
+    const float scale = range > 0.f ? 255.999f / range : 0.f;       // monotone map of [flo, fhi] onto bins 0..255
+    int bin[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = u * 32 + lane;
+        bin[u] = max(0, min(255, (int)((fv[u] - flo) * scale)));
+        if (i < n) atomicAdd(&hist[bin[u]], 1u);
     }
     __syncwarp();
-    warp_bitonic_sort_u64(stage, CAP, lane);
-    if (n >= kprime) {
-        for (int i = lane; i < kprime; i += 32) gbuf[i] = stage[i];
-        new_cnt = kprime;
-        new_tau = sortable_to_float((uint32_t)(stage[kprime - 1] >> 32));
-    } else {
-        for (int i = lane; i < n; i += 32) gbuf[i] = stage[i];
-        new_cnt = n;
-        new_tau = CUDART_INF_F;
+    // prefix over the 256 bins: each lane owns 8 consecutive bins
+    const uint4 h0 = reinterpret_cast<const uint4*>(hist)[lane * 2];
+    const uint4 h1 = reinterpret_cast<const uint4*>(hist)[lane * 2 + 1];
+    const uint32_t c[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    uint32_t mine = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mine += c[e];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
+    // first lane whose inclusive prefix reaches kprime holds the cut bin
+    const unsigned reach = __ballot_sync(0xffffffffu, incl >= (uint32_t)kprime);
+    int cut_bin = 255;
+    uint32_t kept = (uint32_t)n;
+    if (reach) {
+        const int owner = __ffs(reach) - 1;
+        uint32_t run = incl - mine;
+        int b = 7;
+        uint32_t k_at = 0;
+        bool found = false;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            run += c[e];
+            if (!found && run >= (uint32_t)kprime) { found = true; b = e; k_at = run; }
+        }
+        cut_bin = __shfl_sync(0xffffffffu, lane * 8 + b, owner);
+        kept = __shfl_sync(0xffffffffu, k_at, owner);
+    }
+    if ((int)kept > max_keep) {
+        uint32_t ss[4], pp[4];
+        compact_sort(gbuf, n, lane, kprime, ss, pp, nc, nt);
+        return;
+    }
+    // stream-compact the kept keys to the front (all keys are in registers: in-place is safe)
+    uint32_t base = 0;
+    float tmax = -CUDART_INF_F;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = u * 32 + lane;
+        const bool keep = i < n && bin[u] <= cut_bin;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            gbuf[base + __popc(m & ((1u << lane) - 1u))] = ((unsigned long long)__float_as_uint(fv[u]) << 32) | pl[u];
+            tmax = fmaxf(tmax, fv[u]);
+        }
+        base += __popc(m);
+    }
+    tmax = sortable_to_float(__reduce_max_sync(0xffffffffu, float_to_sortable(tmax)));
+    nc = (int)kept;
+    nt = reach ? tmax : CUDART_INF_F;
     __syncwarp();
+}
+
+// 32 freshly loaded scores of one query: reduce with FMNMX3 and append the ones below tau
+__device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid_cols, uint32_t col0, float tau,
+                                             unsigned long long* mybuf, int& cnt) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vr[i]);
+    if (valid_cols < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i >= valid_cols) v[i] = CUDART_INF_F;
+    }
+    float g4[4];
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+        const float a = ptx::min3(v[8 * gi], v[8 * gi + 1], v[8 * gi + 2]);
+        const float b = ptx::min3(v[8 * gi + 3], v[8 * gi + 4], v[8 * gi + 5]);
+        g4[gi] = ptx::min3(a, b, fminf(v[8 * gi + 6], v[8 * gi + 7]));
+    }
+    const float m = fminf(fminf(g4[0], g4[1]), fminf(g4[2], g4[3]));
+    if (m < tau) {
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+            if (g4[gi] < tau) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (v[8 * gi + i] < tau) {
+                        mybuf[cnt] = make_key(v[8 * gi + i], col0 + 8 * gi + i);
+                        ++cnt;
+                    }
+                }
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p) {
@@ -219,8 +400,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
 
     if (threadIdx.x == 0) {
         ptx::mbar_init(&bars->a_full, 1);
-        ptx::mbar_init(&bars->a_empty, 1);
-        for (int s = 0; s < 4; ++s) { ptx::mbar_init(&bars->b_full[s], 1); ptx::mbar_init(&bars->b_empty[s], 1); }
+        ptx::mbar_init(&bars->a_empty, NQ);
+        for (int s = 0; s < 4; ++s) { ptx::mbar_init(&bars->b_full[s], 1); ptx::mbar_init(&bars->b_empty[s], NQ); }
         for (int q = 0; q < NQ; ++q) { ptx::mbar_init(&bars->acc_full[q], 1); ptx::mbar_init(&bars->acc_empty[q], 4); }
         ptx::fence_barrier_init();
     }
@@ -229,6 +410,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    const int my_items = p.n_items > (int)blockIdx.x ? (p.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t total_tiles = (uint32_t)my_items * (uint32_t)p.n_rtiles;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -256,31 +439,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // Each query tile q advances through the reference tiles on its own counter tq[q]; the
+        // issuer serves whichever q has both its operand stage and its accumulator available, so
+        // a warpgroup busy compacting does not hold up the other two (bounded by the ring depth).
         if (lane == 0) {
             const uint32_t idesc = ptx::make_idesc_f16(TILE, TILE);
             const uint32_t lbo = TILE * 16, sbo = 128;
-            uint32_t t = 0, it = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-                ptx::mbar_wait(&bars->a_full, it & 1);
-                for (int j = 0; j < p.n_rtiles; ++j, ++t) {
-                    const uint32_t s = t % p.stages, use = t / p.stages;
-                    ptx::mbar_wait(&bars->b_full[s], use & 1);
+            uint32_t tq0 = 0, tq1 = 0, tq2 = 0;            // NQ == 3 tile counters, kept in registers
+            uint32_t done = 0;
+            int q = 0;
+            while (done < NQ * total_tiles) {
+                const uint32_t t = q == 0 ? tq0 : (q == 1 ? tq1 : tq2);
+                bool ready = t < total_tiles;
+                const uint32_t it = t / (uint32_t)p.n_rtiles;
+                const uint32_t s = t % p.stages, use = t / p.stages;
+                // non-blocking probes: a warpgroup that is not ready must not delay the others
+                ready = ready && ptx::mbar_test_wait(&bars->acc_empty[q], (t & 1) ^ 1);
+                ready = ready && ptx::mbar_test_wait(&bars->b_full[s], use & 1);
+                ready = ready && ptx::mbar_test_wait(&bars->a_full, it & 1);
+                if (ready) {
                     ptx::tc_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem + p.a_off) + q * a_tile_bytes;
                     const uint32_t b_addr = ptx::smem_u32(smem + p.b_off) + s * a_tile_bytes;
-                    for (int q = 0; q < NQ; ++q) {
-                        ptx::mbar_wait(&bars->acc_empty[q], (t & 1) ^ 1);
-                        ptx::tc_fence_after();
-                        const uint32_t a_addr = ptx::smem_u32(smem + p.a_off) + q * a_tile_bytes;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t ad = ptx::make_smem_desc(a_addr + ks * 2 * lbo, lbo, sbo);
-                            const uint64_t bd = ptx::make_smem_desc(b_addr + ks * 2 * lbo, lbo, sbo);
-                            ptx::mma_f16_ss(tmem_base + q * TILE, ad, bd, idesc, ks > 0 ? 1u : 0u);
-                        }
-                        ptx::mma_commit(&bars->acc_full[q]);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t ad = ptx::make_smem_desc(a_addr + ks * 2 * lbo, lbo, sbo);
+                        const uint64_t bd = ptx::make_smem_desc(b_addr + ks * 2 * lbo, lbo, sbo);
+                        ptx::mma_f16_ss(tmem_base + q * TILE, ad, bd, idesc, ks > 0 ? 1u : 0u);
                     }
+                    ptx::mma_commit(&bars->acc_full[q]);
                     ptx::mma_commit(&bars->b_empty[s]);
+                    if ((t + 1) % (uint32_t)p.n_rtiles == 0) ptx::mma_commit(&bars->a_empty);   // last tile of an item
+                    if (q == 0) tq0 = t + 1; else if (q == 1) tq1 = t + 1; else tq2 = t + 1;
+                    ++done;
                 }
-                ptx::mma_commit(&bars->a_empty);
+                q = (q + 1 == NQ) ? 0 : q + 1;
             }
         }
     } else if (warp >= EPI_WARP0) {
@@ -288,10 +480,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         const int q = (warp - EPI_WARP0) >> 2;            // query tile of this warpgroup
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;
-        unsigned long long* stage = reinterpret_cast<unsigned long long*>(smem + p.sort_off) + (size_t)(warp - EPI_WARP0) * CAP;
         unsigned long long* mybuf = p.cand_buf + ((size_t)blockIdx.x * NQ * TILE + q * TILE + row) * CAP;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + q * TILE;
         uint32_t t = 0;
+        uint32_t ks[4], kpl[4];
+        uint32_t* hist = reinterpret_cast<uint32_t*>(smem + p.sort_off) + (size_t)(warp - EPI_WARP0) * 256;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             float tau = CUDART_INF_F;
             int cnt = 0;
@@ -310,38 +503,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[q]);
                     }
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vr[i]);
-                    if (col_limit < (c + 1) * CHUNK) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * CHUNK + i >= col_limit) v[i] = CUDART_INF_F;
-                    }
-                    float g4[4];
-#pragma unroll
-                    for (int gi = 0; gi < 4; ++gi) {
-                        const float a = ptx::min3(v[8 * gi], v[8 * gi + 1], v[8 * gi + 2]);
-                        const float b = ptx::min3(v[8 * gi + 3], v[8 * gi + 4], v[8 * gi + 5]);
-                        g4[gi] = ptx::min3(a, b, fminf(v[8 * gi + 6], v[8 * gi + 7]));
-                    }
-                    const float m = fminf(fminf(g4[0], g4[1]), fminf(g4[2], g4[3]));
-                    if (m < tau) {
-                        const uint32_t col0 = (uint32_t)(j * TILE + c * CHUNK);
-#pragma unroll
-                        for (int gi = 0; gi < 4; ++gi) {
-                            if (g4[gi] < tau) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    if (v[8 * gi + i] < tau) {
-                                        mybuf[cnt] = make_key(v[8 * gi + i], col0 + 8 * gi + i);
-                                        ++cnt;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - CHUNK);
+                    filter_chunk(vr, col_limit - c * CHUNK, (uint32_t)(j * TILE + c * CHUNK), tau, mybuf, cnt);
+                    // hard limit: the next chunk may append 32 more; soft limit once per tile, after the release
+                    const int lim = c == TILE / CHUNK - 1 ? p.soft : CAP - CHUNK;
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > lim);
                     while (need) {
                         const int src = __ffs(need) - 1;
                         need &= need - 1;
@@ -350,7 +515,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                         const int n = __shfl_sync(0xffffffffu, cnt, src);
                         int nc;
                         float nt;
-                        compact_buffer(gb, n, stage, lane, p.kprime, nc, nt);
+                        compact_select(gb, n, lane, p.kprime, p.soft - 8, hist, nc, nt);
                         if (lane == src) { cnt = nc; tau = nt; }
                     }
                 }
@@ -363,14 +528,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                 const float old_tau = __shfl_sync(0xffffffffu, tau, src);
                 int nc;
                 float nt;
-                compact_buffer(gb, n, stage, lane, p.kprime, nc, nt);
+                compact_sort(gb, n, lane, p.kprime, ks, kpl, nc, nt);
                 const long long qg = (long long)item * NQ * TILE + q * TILE + quarter * 32 + src;
                 if (qg < p.n_query) {
-                    for (int i = lane; i < p.kc_out; i += 32)
-                        p.cand_idx[qg * p.kc_out + i] = i < nc ? (int32_t)(uint32_t)(stage[i] & 0xffffffffull) : -1;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = u * 32 + lane;
+                        if (i < p.kc_out) p.cand_idx[qg * p.kc_out + i] = i < nc ? (int32_t)kpl[u] : -1;
+                    }
                     if (lane == 0) p.cert_tau[qg] = n >= p.kprime ? nt : old_tau;
                 }
-                __syncwarp();
             }
         }
     }
@@ -464,6 +631,7 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     p.stages = pl.stages; p.kprime = kprime; p.kc_out = kprime;
     p.cand_buf = cbuf; p.cand_idx = cand; p.cert_tau = tau;
     p.a_off = pl.a_off; p.b_off = pl.b_off; p.sort_off = pl.sort_off; p.bar_off = pl.bar_off;
+    p.soft = tc::CAP - tc::CHUNK - 16 > kprime ? tc::CAP - tc::CHUNK - 16 : kprime;
     NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
     tc::candidates_kernel<<<grid, tc::NTHREADS, pl.total, st>>>(p);
     NABO_LAUNCH_CHECK("candidates_kernel");
