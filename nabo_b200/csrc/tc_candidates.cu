@@ -12,9 +12,8 @@
 //
 // CTA = 512 threads, persistent over work items of NQ=3 query tiles (384 queries):
 //   warps 0-11  epilogue: warpgroup w owns query tile w; thread = one query row (TMEM lane)
-//   warp 12  TMA producer: A tiles once per item, B (reference) tiles through a ring
-//   warp 13  MMA issuer : serves whichever query tile has operands + accumulator ready
-//   warp 14  TMEM allocator
+//   warp 12  TMEM allocator, then TMA producer: A tiles once per item, B (reference) tiles through a ring
+//   warps 13-15  one MMA issuer thread per query tile, each asleep on its own accumulator barrier
 // The epilogue keeps, per query, a running threshold tau (register) and a private
 // candidate buffer of CAP keys in L2-resident global memory; a tile chunk is first reduced
 // with FMNMX3 and only chunks holding a score < tau take the append path.  When a buffer
@@ -34,8 +33,9 @@ constexpr int NQ = 3;               // query tiles per work item
 constexpr int NTHREADS = 512;
 constexpr int N_EPI_WARPS = 4 * NQ;  // warps 0..11: epilogue (TMEM lane quarter = warp % 4)
 constexpr int PRODUCER_WARP = 12;    // highest warp ids on their schedulers: the arbiter favours them,
-constexpr int MMA_WARP = 13;         // so the single-thread producer / issuer are never starved
-constexpr int TMEM_WARP = 14;
+constexpr int MMA_WARP0 = 13;        // so the single-thread producer / issuers are never starved;
+                                     // warps 13..15: one MMA issuer per query tile (no polling loop)
+constexpr int TMEM_WARP = 12;
 constexpr int CAP = 128;            // candidate buffer entries per query
 constexpr int CHUNK = 32;           // columns per tcgen05.ld
 
@@ -440,32 +440,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                 }
             }
         }
-    } else if (warp == MMA_WARP) {
-        // ===================== MMA issuer =====================
-        // Each query tile q advances through the reference tiles on its own counter tq[q]; the
-        // issuer serves whichever q has both its operand stage and its accumulator available, so
-        // a warpgroup busy compacting does not hold up the other two (bounded by the ring depth).
+    } else if (warp >= MMA_WARP0 && warp < MMA_WARP0 + NQ) {
+        // ===================== MMA issuers: one thread per query tile =====================
+        // Each issuer sleeps on its own accumulator's mbarrier (hardware wake-up, no polling loop), so a
+        // warpgroup that is busy compacting never delays the other two; the tensor pipe interleaves the
+        // three instruction streams.  An operand stage is released when all NQ issuers have consumed it.
         if (lane == 0) {
+            const int q = warp - MMA_WARP0;
             const uint32_t idesc = ptx::make_idesc_f16(TILE, TILE);
             const uint32_t lbo = TILE * 16, sbo = 128;
-            uint32_t tq0 = 0, tq1 = 0, tq2 = 0;            // NQ == 3 tile counters, kept in registers
-            uint32_t done = 0;
-            int q = 0;
-            while (done < NQ * total_tiles) {
-                const uint32_t t = q == 0 ? tq0 : (q == 1 ? tq1 : tq2);
-                bool ready = t < total_tiles;
-                const uint32_t it = t / (uint32_t)p.n_rtiles;
-                const uint32_t s = t % p.stages, use = t / p.stages;
-                // non-blocking probes: a warpgroup that is not ready must not delay the others
-                ready = ready && ptx::mbar_test_wait(&bars->acc_empty[q], (t & 1) ^ 1);
-                ready = ready && ptx::mbar_test_wait(&bars->b_full[s], use & 1);
-                ready = ready && ptx::mbar_test_wait(&bars->a_full, it & 1);
-                if (ready) {
+            const uint32_t d_tmem = tmem_base + q * TILE;
+            const uint64_t ad0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.a_off) + q * a_tile_bytes, lbo, sbo);
+            const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off), lbo, sbo);
+            uint32_t t = 0, it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+                ptx::mbar_wait(&bars->a_full, it & 1);
+                for (int j = 0; j < p.n_rtiles; ++j, ++t) {
+                    const uint32_t s = t % p.stages, use = t / p.stages;
+                    ptx::mbar_wait(&bars->acc_empty[q], (t & 1) ^ 1);
+                    ptx::mbar_wait(&bars->b_full[s], use & 1);
                     ptx::tc_fence_after();
                     // descriptors differ only in the start-address field (16-byte units): one K step = 2 * LBO
-                    uint64_t ad = ptx::make_smem_desc(ptx::smem_u32(smem + p.a_off) + q * a_tile_bytes, lbo, sbo);
-                    uint64_t bd = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off) + s * a_tile_bytes, lbo, sbo);
-                    const uint32_t d_tmem = tmem_base + q * TILE;
+                    uint64_t ad = ad0;
+                    uint64_t bd = bd0 + (uint64_t)((s * a_tile_bytes) >> 4);
+#pragma unroll 2
                     for (int ks = 0; ks < ksteps; ++ks) {
                         ptx::mma_f16_ss(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
                         ad += (2 * lbo) >> 4;
@@ -473,11 +471,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                     }
                     ptx::mma_commit(&bars->acc_full[q]);
                     ptx::mma_commit(&bars->b_empty[s]);
-                    if ((t + 1) % (uint32_t)p.n_rtiles == 0) ptx::mma_commit(&bars->a_empty);   // last tile of an item
-                    if (q == 0) tq0 = t + 1; else if (q == 1) tq1 = t + 1; else tq2 = t + 1;
-                    ++done;
                 }
-                q = (q + 1 == NQ) ? 0 : q + 1;
+                ptx::mma_commit(&bars->a_empty);
             }
         }
     } else if (warp < N_EPI_WARPS) {

@@ -3,7 +3,8 @@ import sys
 import torch
 sys.path.insert(0, ".")
 from nabo_b200 import core, synth
-n, m, g, k = 148 * 384, 131072, 50, 30
+import os
+n, m, g, k = 148 * 384, int(os.environ.get("PROF_M", "131072")), 50, 30
 q = torch.from_numpy(synth.pc_mixture(n, g, 101)).cuda()
 r = torch.from_numpy(synth.pc_mixture(m, g, 1)).cuda()
 for _ in range(2):
