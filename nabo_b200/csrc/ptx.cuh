@@ -124,6 +124,17 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_f16(int m, int n) {
            | ((uint32_t)(m >> 4) << 24);   // m_dim
 }
 
+// true on exactly one (elected) lane of a fully active warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ float min3(float a, float b, float c) {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));

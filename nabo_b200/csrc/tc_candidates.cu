@@ -394,6 +394,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid
     }
 }
 
+template <int KSTEPS>   // K steps of 16 known at compile time (0 = runtime loop)
 __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     Barriers* bars = reinterpret_cast<Barriers*>(smem + p.bar_off);
@@ -445,7 +446,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         // Each issuer sleeps on its own accumulator's mbarrier (hardware wake-up, no polling loop), so a
         // warpgroup that is busy compacting never delays the other two; the tensor pipe interleaves the
         // three instruction streams.  An operand stage is released when all NQ issuers have consumed it.
-        if (lane == 0) {
+        // The whole warp runs the loop so that descriptor arithmetic stays in the uniform datapath (no
+        // per-instruction R2UR traffic); only the elected lane issues tcgen05.mma / commit.
+        {
             const int q = warp - MMA_WARP0;
             const uint32_t idesc = ptx::make_idesc_f16(TILE, TILE);
             const uint32_t lbo = TILE * 16, sbo = 128;
@@ -461,18 +464,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                     ptx::mbar_wait(&bars->b_full[s], use & 1);
                     ptx::tc_fence_after();
                     // descriptors differ only in the start-address field (16-byte units): one K step = 2 * LBO
-                    uint64_t ad = ad0;
-                    uint64_t bd = bd0 + (uint64_t)((s * a_tile_bytes) >> 4);
-#pragma unroll 2
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        ptx::mma_f16_ss(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
-                        ad += (2 * lbo) >> 4;
-                        bd += (2 * lbo) >> 4;
+                    const uint64_t bd1 = bd0 + (uint64_t)((s * a_tile_bytes) >> 4);
+                    if (ptx::elect_one()) {
+                        if (KSTEPS > 0) {
+#pragma unroll
+                            for (int ks = 0; ks < KSTEPS; ++ks)
+                                ptx::mma_f16_ss(d_tmem, ad0 + ks * ((2 * lbo) >> 4), bd1 + ks * ((2 * lbo) >> 4), idesc,
+                                                ks > 0 ? 1u : 0u);
+                        } else {
+                            for (int ks = 0; ks < ksteps; ++ks)
+                                ptx::mma_f16_ss(d_tmem, ad0 + ks * ((2 * lbo) >> 4), bd1 + ks * ((2 * lbo) >> 4), idesc,
+                                                ks > 0 ? 1u : 0u);
+                        }
+                        ptx::mma_commit(&bars->acc_full[q]);
+                        ptx::mma_commit(&bars->b_empty[s]);
+                        if (j == p.n_rtiles - 1) ptx::mma_commit(&bars->a_empty);
                     }
-                    ptx::mma_commit(&bars->acc_full[q]);
-                    ptx::mma_commit(&bars->b_empty[s]);
+                    __syncwarp();
                 }
-                ptx::mma_commit(&bars->a_empty);
             }
         }
     } else if (warp < N_EPI_WARPS) {
@@ -632,8 +641,16 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     p.cand_buf = cbuf; p.cand_idx = cand; p.cert_tau = tau;
     p.a_off = pl.a_off; p.b_off = pl.b_off; p.sort_off = pl.sort_off; p.bar_off = pl.bar_off;
     p.soft = tc::CAP - tc::CHUNK - 16 > kprime ? tc::CAP - tc::CHUNK - 16 : kprime;
-    NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
-    tc::candidates_kernel<<<grid, tc::NTHREADS, pl.total, st>>>(p);
+#define NABO_TC_LAUNCH(KS)                                                                                          \
+    do {                                                                                                           \
+        NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                       (int)pl.total));                                                            \
+        tc::candidates_kernel<KS><<<grid, tc::NTHREADS, pl.total, st>>>(p);                                        \
+    } while (0)
+    if (kp == 160) NABO_TC_LAUNCH(10);        // g = 50 (BASELINE configs 2-5)
+    else if (kp == 80) NABO_TC_LAUNCH(5);     // g = 25 (config 1)
+    else NABO_TC_LAUNCH(0);
+#undef NABO_TC_LAUNCH
     NABO_LAUNCH_CHECK("candidates_kernel");
     tm.end(0);
     *cand_idx_out = cand; *kprime_out = kprime; *cert_tau_out = tau; *qn2_out = qn2; *scal_out = scal;
