@@ -7,37 +7,57 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------ SNN counts + weights
-// One warp per query.  A = the query's k neighbours (shared memory); for neighbour j the
-// lanes stride over row ref_knn[j][:k_use] and test membership in A.
+// One warp per query.  A = the query's k neighbours, sorted once in shared memory; the k x k_use
+// entries of the neighbours' own kNN rows are spread over the lanes (coalesced row reads) and each
+// is looked up in A by binary search; per-row hit counts accumulate in shared memory.
 __global__ void __launch_bounds__(256)
-snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, const int32_t* __restrict__ ref_knn,
+snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int kp2, const int32_t* __restrict__ ref_knn,
            int n_ref, int k_ref, int k_use, const double* __restrict__ lut, uint8_t* __restrict__ counts,
            double* __restrict__ weights) {
-    extern __shared__ int sm_a[];
+    extern __shared__ int sm_snn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x * 8 + warp;
     if (t >= n_query) return;
-    int* a = sm_a + warp * k;
-    for (int i = lane; i < k; i += 32) a[i] = tgt_knn[(long long)t * k + i];
+    int* a_sorted = sm_snn + warp * (2 * kp2 + k);      // [kp2] sorted keys
+    int* a_aux = a_sorted + kp2;                         // [kp2] scratch for the sort (values unused)
+    int* hits = a_aux + kp2;                             // [k]   per-neighbour intersection size
+    for (int i = lane; i < kp2; i += 32) {
+        const int v = i < k ? tgt_knn[(long long)t * k + i] : -1;
+        a_sorted[i] = v >= 0 ? v : 0x7fffffff;           // missing neighbours never match
+        a_aux[i] = i;
+    }
+    for (int i = lane; i < k; i += 32) hits[i] = 0;
     __syncwarp();
-    for (int jj = 0; jj < k; ++jj) {
-        const int j = a[jj];
-        int c = 0;
-        if (j >= 0 && j < n_ref) {
-            const int32_t* row = ref_knn + (long long)j * k_ref;
-            for (int l = lane; l < k_use; l += 32) {
-                const int b = row[l];
-                bool hit = false;
-                if (b >= 0)
-                    for (int i = 0; i < k; ++i) hit |= (a[i] == b);
-                c += hit;
+    // bitonic sort of the keys (ascending)
+    for (int size = 2; size <= kp2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int e = lane; e < (kp2 >> 1); e += 32) {
+                const int lo = 2 * e - (e & (stride - 1)), hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const int x = a_sorted[lo], y = a_sorted[hi];
+                if (up ? (y < x) : (x < y)) { a_sorted[lo] = y; a_sorted[hi] = x; }
             }
+            __syncwarp();
         }
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0) {
-            if (counts) counts[(long long)t * k + jj] = (uint8_t)c;
-            if (weights) weights[(long long)t * k + jj] = lut[c];
+    const int total = k * k_use;
+    for (int e = lane; e < total; e += 32) {
+        const int row = e / k_use, col = e - row * k_use;
+        const int j = tgt_knn[(long long)t * k + row];
+        if (j < 0 || j >= n_ref) continue;
+        const int b = ref_knn[(long long)j * k_ref + col];
+        if (b < 0) continue;
+        int lo = 0, hi = kp2;                            // first position with a_sorted[pos] >= b
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (a_sorted[mid] < b) lo = mid + 1; else hi = mid;
         }
+        if (lo < kp2 && a_sorted[lo] == b) atomicAdd(&hits[row], 1);
+    }
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+        const int c = hits[i];
+        if (counts) counts[(long long)t * k + i] = (uint8_t)c;
+        if (weights) weights[(long long)t * k + i] = lut[c];
     }
 }
 
@@ -50,8 +70,10 @@ extern "C" int nabo_snn_weights(const int32_t* tgt_knn, int n_query, int k, cons
     NABO_ARG(tgt_knn && ref_knn && (out_counts || out_weights), "snn: null pointer");
     NABO_ARG(!out_weights || lut, "snn: weights requested without a lut");
     int k_use = k < k_ref ? k : k_ref;   // ref_data[ref_c][:k], _mapping.py:193
-    snn_kernel<<<(n_query + 7) / 8, 256, 8 * k * sizeof(int), (cudaStream_t)stream>>>(
-        tgt_knn, n_query, k, ref_knn, n_ref, k_ref, k_use, lut, out_counts, out_weights);
+    int kp2 = nabo_next_pow2(k);
+    if (kp2 < 2) kp2 = 2;
+    snn_kernel<<<(n_query + 7) / 8, 256, 8 * (2 * kp2 + k) * sizeof(int), (cudaStream_t)stream>>>(
+        tgt_knn, n_query, k, kp2, ref_knn, n_ref, k_ref, k_use, lut, out_counts, out_weights);
     NABO_LAUNCH_CHECK("snn_kernel");
     return 0;
 }
@@ -75,39 +97,60 @@ rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, uint32_t* __
     hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];   // digit-major
 }
 
-// exclusive scan of `n` counters by one block (n up to a few million)
-__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t* __restrict__ a, long long n) {
-    __shared__ uint32_t part[1024];
-    const long long per = (n + 1023) / 1024;
-    const long long lo = (long long)threadIdx.x * per;
-    const long long hi = lo + per < n ? lo + per : n;
-    uint32_t s = 0;
-    for (long long i = lo; i < hi; ++i) s += a[i];
-    part[threadIdx.x] = s;
+// Exclusive scan of the digit-major counter matrix hist[256][nblocks] in two parallel steps:
+//   (1) one block per digit: exclusive scan of that digit's row, row total -> totals[d]
+//   (2) the scatter kernel adds the exclusive prefix of totals[] (256 values, scanned per block there)
+__global__ void __launch_bounds__(256) rs_scan_rows_kernel(uint32_t* __restrict__ hist, int nblocks,
+                                                           uint32_t* __restrict__ totals) {
+    __shared__ uint32_t warp_sum[8];
+    __shared__ uint32_t carry_s;
+    uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    // Hillis-Steele over the 1024 partials
-    for (int o = 1; o < 1024; o <<= 1) {
-        uint32_t v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    for (int base = 0; base < nblocks; base += 256) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? row[i] : 0;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
         __syncthreads();
-        part[threadIdx.x] += v;
+        uint32_t before = carry_s;
+        for (int w = 0; w < warp; ++w) before += warp_sum[w];
+        if (i < nblocks) row[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = before + incl;
         __syncthreads();
     }
-    uint32_t run = threadIdx.x ? part[threadIdx.x - 1] : 0;
-    for (long long i = lo; i < hi; ++i) {
-        uint32_t v = a[i];
-        a[i] = run;
-        run += v;
-    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, int n, int shift,
-                  const uint32_t* __restrict__ offs, int nblocks, uint32_t* __restrict__ okeys,
-                  uint32_t* __restrict__ ovals) {
+                  const uint32_t* __restrict__ offs, const uint32_t* __restrict__ totals, int nblocks,
+                  uint32_t* __restrict__ okeys, uint32_t* __restrict__ ovals) {
     __shared__ uint32_t running[256];           // elements of each digit placed by earlier rounds
     __shared__ uint16_t wcnt[RS_THREADS / 32][256];
+    __shared__ uint32_t wtot[RS_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    running[threadIdx.x] = offs[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    {   // exclusive prefix of the 256 digit totals (thread = digit)
+        const uint32_t v = totals[threadIdx.x];
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+        for (int w = 0; w < warp; ++w) before += wtot[w];
+        running[threadIdx.x] = before + incl - v + offs[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    }
     const long long base = (long long)blockIdx.x * RS_BLOCK;
     for (int r = 0; r < RS_ROUNDS; ++r) {
         for (int w = 0; w < RS_THREADS / 32; ++w) wcnt[w][threadIdx.x] = 0;
@@ -181,7 +224,7 @@ extern "C" size_t nabo_scores_workspace_bytes(int n_query, int k, int n_ref) {
     size_t e = (size_t)n_query * (size_t)k;
     size_t nblocks = (e + RS_BLOCK - 1) / RS_BLOCK;
     (void)n_ref;
-    return 4 * nabo_align_up(e * sizeof(uint32_t), 256) + nabo_align_up(256 * nblocks * sizeof(uint32_t), 256) + 1024;
+    return 4 * nabo_align_up(e * sizeof(uint32_t), 256) + nabo_align_up(256 * nblocks * sizeof(uint32_t), 256) + 4096;
 }
 
 extern "C" int nabo_mapping_scores(const int32_t* tgt_knn, const uint8_t* counts, const double* lut, int n_query,
@@ -208,6 +251,7 @@ extern "C" int nabo_mapping_scores(const int32_t* tgt_knn, const uint8_t* counts
     uint32_t* k1 = ar.take<uint32_t>(e);
     uint32_t* v1 = ar.take<uint32_t>(e);
     uint32_t* hist = ar.take<uint32_t>((size_t)256 * nblocks);
+    uint32_t* totals = ar.take<uint32_t>(256);
     if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "scores: workspace too small");
     score_edges_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(tgt_knn, counts, lut, e, k, n_ref, include,
                                                                    min_weight, weighted, k0, v0);
@@ -216,8 +260,8 @@ extern "C" int nabo_mapping_scores(const int32_t* tgt_knn, const uint8_t* counts
     while ((1ll << bits) <= n_ref) ++bits;          // keys go up to n_ref inclusive
     for (int shift = 0; shift < bits; shift += 8) {
         rs_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(k0, (int)e, shift, hist, nblocks);
-        rs_scan_kernel<<<1, 1024, 0, st>>>(hist, (long long)256 * nblocks);
-        rs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(k0, v0, (int)e, shift, hist, nblocks, k1, v1);
+        rs_scan_rows_kernel<<<256, 256, 0, st>>>(hist, nblocks, totals);
+        rs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(k0, v0, (int)e, shift, hist, totals, nblocks, k1, v1);
         NABO_LAUNCH_CHECK("radix pass");
         uint32_t* t = k0; k0 = k1; k1 = t;
         t = v0; v0 = v1; v1 = t;
