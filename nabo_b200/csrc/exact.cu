@@ -388,8 +388,8 @@ int nabo_knn_exact_launch(const double* q, int ldq, const double* r, int ldr, in
 // the row passes iff its ksel-th exact distance is strictly below L(q).  Rows that fail are
 // appended to fail_rows for the exact brute-force engine.
 __device__ __forceinline__ double cert_lower_bound(const NaboCert& c, int qi, float tau) {
+    if (c.kind == NABO_CERT_LINEAR) return (double)tau - c.c_acc;     // score = lower bound of the distance
     const double sc_inv = c.scal[1], rmax = c.scal[2];
-    if (c.kind == NABO_CERT_LINEAR) return (double)tau - c.c_acc;
     const double qn2 = c.qn2[qi];
     const double qn = sqrt(qn2);
     const double eps = c.c_acc * (4.0 * qn * rmax + rmax * rmax + qn2);       // accumulation error (scaled^2)

@@ -2,7 +2,7 @@
 // for the rows the certificate could not clear.  Results are identical to the exact engine
 // (and hence to the reference) by construction; only the amount of FP64 work changes.
 //   Euclidean / cosine : tensor-core candidate pass (tc_candidates.cu)
-//   modified Canberra  : exact engine (an FP32 CUDA-core candidate pass is the next step)
+//   modified Canberra  : two-phase FP32 CUDA-core candidate pass (canberra_candidates.cu)
 #include "knn_internal.cuh"
 
 // Accumulation-error constant of the tensor-core score relative to (4|q||r| + |r|^2 + |q|^2);
@@ -10,7 +10,9 @@
 static const double kCAcc = 1.52587890625e-05;   // 2^-16
 
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric) {
-    if (metric == NABO_MOD_CANBERRA) return 256;
+    if (metric == NABO_MOD_CANBERRA)
+        return nabo_align_up((size_t)n_query * nabo_cb_kprime(k, 1) * 4, 256) + 3 * nabo_align_up((size_t)n_query * 4, 256) +
+               nabo_align_up(nabo_cb_pretile_floats(n_query, g) * 4, 256) + nabo_align_up(nabo_cb_pretile_floats(n_ref, g) * 4, 256) + 4096;
     return nabo_tc_workspace_bytes(n_query, n_ref, g, k, 1) + nabo_align_up((size_t)n_query * 4, 256) + 1024;
 }
 
@@ -22,6 +24,43 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
     tm.begin();
     const bool use_tc = (metric == NABO_EUCLIDEAN || metric == NABO_COSINE) && nabo_tc_supported(g, k, drop_first) &&
                         n_ref > nabo_tc_kprime(k, drop_first);
+    const bool use_cb = metric == NABO_MOD_CANBERRA && nabo_cb_supported(g, k, drop_first) &&
+                        n_ref > nabo_cb_kprime(k, drop_first);
+    if (use_cb) {
+        if (workspace_bytes < nabo_fast_workspace_bytes(n_query, n_ref, g, k, metric))
+            return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
+        NaboArena ar(workspace, workspace_bytes);
+        const int kprime = nabo_cb_kprime(k, drop_first);
+        int32_t* cand = ar.take<int32_t>((size_t)n_query * kprime);
+        float* tau = ar.take<float>(n_query);
+        int* fail_rows = ar.take<int>(n_query);
+        int* fail_count = ar.take<int>(1);
+        float* qt = ar.take<float>(nabo_cb_pretile_floats(n_query, g));
+        float* rt = ar.take<float>(nabo_cb_pretile_floats(n_ref, g));
+        if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
+        NABO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
+        int rc = nabo_cb_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, qt, rt, cand, tau, st);
+        if (rc) return rc;
+        tm.end(0);
+        NaboCert cert;
+        cert.kind = NABO_CERT_LINEAR; cert.tau = tau; cert.qn2 = nullptr; cert.scal = nullptr; cert.c_acc = nabo_cb_eps(g);
+        rc = nabo_rerank_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset, cand,
+                                kprime, cert, fail_rows, fail_count, out_idx, out_dist, st);
+        if (rc) return rc;
+        tm.end(1);
+        rc = nabo_knn_exact_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
+                                   fail_rows, fail_count, out_idx, out_dist, st);
+        if (rc) return rc;
+        tm.end(2);
+        if (stats_host) {
+            int nfail = 0;
+            NABO_CUDA(cudaMemcpyAsync(&nfail, fail_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+            NABO_CUDA(cudaStreamSynchronize(st));
+            stats_host[0] = n_query; stats_host[1] = nfail; stats_host[2] = kprime; stats_host[3] = 5;
+            stats_host[4] = tm.ns(0); stats_host[5] = tm.ns(1); stats_host[6] = tm.ns(2);
+        }
+        return 0;
+    }
     if (!use_tc) {
         int rc = nabo_knn_exact_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
                                        nullptr, nullptr, out_idx, out_dist, st);

@@ -34,6 +34,14 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
                        int* kprime_out, float** cert_tau_out, double** qn2_out, double** scal_out, int* launches,
                        NaboStageTimer& tm, cudaStream_t st);
 
+bool nabo_cb_supported(int g, int k, int drop_first);
+int nabo_cb_kprime(int k, int drop_first);
+double nabo_cb_eps(int g);
+size_t nabo_cb_pretile_floats(int n, int g);
+int nabo_cb_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
+                       double f, const uint8_t* mask, int drop_first, float* qt, float* rt, int32_t* cand, float* tau,
+                       cudaStream_t st);
+
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric);
 int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                   int metric, double f, const uint8_t* mask, int drop_first, int idx_offset, int32_t* out_idx,

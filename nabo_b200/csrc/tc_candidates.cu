@@ -414,8 +414,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    const int my_items = p.n_items > (int)blockIdx.x ? (p.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const uint32_t total_tiles = (uint32_t)my_items * (uint32_t)p.n_rtiles;
 
     if (warp == PRODUCER_WARP) {
         // ===================== TMA producer =====================

@@ -22,3 +22,9 @@ for n, m in ((100000, 100000), (200000, 1250000)):
         print("fast %-10s %d x %d: %.2f ms  %.3e pairs/s  %.3e queries/s | %s" % (metric, n, m, ms, n * m / ms * 1e3, n / ms * 1e3, st))
         tf = 2.0 * g * n * m / (st["main_kernel_ms"] * 1e-3) / 1e12
         print("   candidate kernel: %.2f ms -> %.1f useful TFLOP/s (2*g per pair), %.1f executed TFLOP/s (K=160)" % (st["main_kernel_ms"], tf, tf * 160 / 50))
+n, m = 100000, 100000
+q = torch.from_numpy(synth.pc_mixture(n, g, 101)).cuda()
+r = torch.from_numpy(synth.pc_mixture(m, g, 1)).cuda()
+ms = t(lambda: core.knn(q, r, k, "mod_canberra", 0.25, mode="fast"), reps=2)
+_, _, st = core.knn(q, r, k, "mod_canberra", 0.25, mode="fast", return_stats=True)
+print("fast mod_canberra %d x %d: %.2f ms  %.3e pairs/s  %.3e queries/s | %s" % (n, m, ms, n * m / ms * 1e3, n / ms * 1e3, st))
