@@ -237,10 +237,19 @@ __global__ void __launch_bounds__(NT, 1)
 knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ r, int ldr, int n_query,
                  int n_ref, int g, int k, double f, const uint8_t* __restrict__ mask, int drop_first,
                  int idx_offset, const int* __restrict__ row_ids, const int* __restrict__ n_rows_dev,
-                 int cap, int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+                 int cap, const NaboExactSplit sp, int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
     extern __shared__ double smem[];
     const ExactSmem s = carve_exact(smem, g, cap);
     const int nq_total = n_rows_dev ? *n_rows_dev : n_query;   // fallback mode: row list on device
+    // fallback for FEW rows: the reference range is split over blockIdx.y and the partial lists are
+    // merged afterwards (mode 1); with many rows the plain row-parallel kernel is used (mode 2)
+    if (sp.mode == 1 && nq_total > sp.f_max) return;
+    if (sp.mode == 2 && nq_total <= sp.f_max) return;
+    const int r_lo = sp.mode == 1 ? (int)((long long)n_ref * blockIdx.y / sp.nsplit) / TR * TR : 0;
+    const int r_hi = sp.mode == 1 ? (blockIdx.y + 1 == (unsigned)sp.nsplit
+                                         ? n_ref
+                                         : (int)((long long)n_ref * (blockIdx.y + 1) / sp.nsplit) / TR * TR)
+                                  : n_ref;
     const int q0 = blockIdx.x * TQ;
     if (q0 >= nq_total) return;
     const int ksel = k + (drop_first ? 1 : 0);
@@ -260,9 +269,9 @@ knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict
         s.nq[threadIdx.x] = acc;
     }
 
-    for (int r0 = 0; r0 < n_ref; r0 += TR) {
+    for (int r0 = r_lo; r0 < r_hi; r0 += TR) {
         __syncthreads();   // previous tile fully consumed (and compaction finished)
-        load_tile_kmajor(s.ys, r, ldr, r0, n_ref, g, nullptr);
+        load_tile_kmajor(s.ys, r, ldr, r0, r_hi, g, nullptr);
         __syncthreads();
         if (METRIC == NABO_COSINE) {
             if (threadIdx.x < TR) {
@@ -298,7 +307,7 @@ knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int j = r0 + tr * 4 + b;
-                if (j >= n_ref) continue;
+                if (j >= r_hi) continue;
                 double d = Pair<METRIC>::finish(acc[a][b], METRIC == NABO_COSINE ? s.nq[ql] : 0.0,
                                                 METRIC == NABO_COSINE ? s.nr[tr * 4 + b] : 0.0);
                 if (d != d || (mask && mask[j])) d = CUDART_INF;   // NaN / ignored -> last
@@ -325,6 +334,16 @@ knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict
             for (int t = n_have + lane; t < cap; t += 32) { d[t] = CUDART_INF; ix[t] = 0x7fffffff; }
             __syncwarp();
             warp_bitonic_sort(d, ix, cap, lane);
+        }
+        if (sp.mode == 1) {
+            // partial list of this reference range: raw keys (NaN / masked = +inf), local indices
+            for (int t = lane; t < ksel; t += 32) {
+                const bool have = t < n_have && t < cap;
+                const size_t o = ((size_t)blockIdx.y * sp.f_max + qi) * ksel + t;
+                sp.part_idx[o] = have ? s.bi[(size_t)ql * cap + t] : -1;
+                sp.part_dist[o] = have ? s.bd[(size_t)ql * cap + t] : CUDART_INF;
+            }
+            continue;
         }
         const long long orow = row_ids ? row_ids[qi] : qi;
         const int skip = drop_first ? 1 : 0;
@@ -355,10 +374,106 @@ static int exact_cap_for(int ksel) {
     return cap;
 }
 
+// merge the per-range partial lists of the split fallback: one warp per failing row
+__global__ void __launch_bounds__(128)
+fallback_merge_kernel(const NaboExactSplit sp, const int* __restrict__ row_ids, const int* __restrict__ n_rows_dev,
+                      int k, int drop_first, int idx_offset, const uint8_t* __restrict__ mask, int capp,
+                      int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    extern __shared__ double smem[];
+    const int n_rows = *n_rows_dev;
+    if (n_rows > sp.f_max) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = blockIdx.x * 4 + warp;
+    if (qi >= n_rows) return;
+    const int ksel = k + (drop_first ? 1 : 0);
+    double* d = smem + (size_t)warp * capp;
+    int* ix = (int*)(smem + (size_t)4 * capp) + (size_t)warp * capp;
+    const int tot = sp.nsplit * ksel;
+    int n_valid = 0;
+    for (int c = lane; c < capp; c += 32) {
+        double dv = CUDART_INF;
+        int id = 0x7fffffff;
+        if (c < tot) {
+            const int sidx = c / ksel, j = c - sidx * ksel;
+            const size_t o = ((size_t)sidx * sp.f_max + qi) * ksel + j;
+            const int i0 = sp.part_idx[o];
+            if (i0 >= 0) { id = i0; dv = sp.part_dist[o]; ++n_valid; }
+        }
+        d[c] = dv; ix[c] = id;
+    }
+    for (int o = 16; o > 0; o >>= 1) n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+    __syncwarp();
+    warp_bitonic_sort(d, ix, capp, lane);
+    const long long orow = row_ids[qi];
+    const int skip = drop_first ? 1 : 0;
+    for (int t = lane; t < k; t += 32) {
+        const int src = t + skip;
+        int id = -1;
+        double dv = CUDART_NAN;
+        if (src < n_valid) {
+            id = ix[src];
+            dv = d[src];
+            if (dv == CUDART_INF || (mask && mask[id])) dv = CUDART_NAN;
+            id += idx_offset;
+        }
+        out_idx[orow * k + t] = id;
+        out_dist[orow * k + t] = dv;
+    }
+}
+
+int nabo_exact_split_count(int ksel) {
+    int s = 2048 / ksel;
+    return s > 48 ? 48 : (s < 1 ? 1 : s);
+}
+size_t nabo_exact_split_workspace(int ksel) {
+    (void)ksel;   // nsplit * ksel <= 2048 for every ksel: one bound, monotone in nothing
+    return (size_t)2048 * NABO_FALLBACK_SPLIT_ROWS * (sizeof(int32_t) + sizeof(double)) + 512;
+}
+
+// Exact engine on the rows listed in row_ids[0 .. *n_rows_dev): split over the reference when the rows
+// are few (one block would otherwise scan the whole reference alone), row-parallel otherwise.  Both
+// variants are launched; each checks the device-side row count and exits at once if it is not its turn,
+// so no host synchronisation is needed.
+int nabo_knn_exact_fallback(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
+                            int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
+                            const int* row_ids, const int* n_rows_dev, void* split_ws, int32_t* out_idx,
+                            double* out_dist, cudaStream_t st) {
+    const int ksel = k + (drop_first ? 1 : 0);
+    NaboExactSplit sp;
+    sp.mode = 1;
+    sp.nsplit = nabo_exact_split_count(ksel);
+    sp.f_max = NABO_FALLBACK_SPLIT_ROWS;
+    sp.part_dist = (double*)split_ws;
+    sp.part_idx = (int32_t*)(sp.part_dist + (size_t)sp.nsplit * sp.f_max * ksel);
+    int rc = nabo_knn_exact_launch_ex(q, ldq, r, ldr, NABO_FALLBACK_SPLIT_ROWS, n_ref, g, ksel, metric, f, mask, 0, 0,
+                                      row_ids, n_rows_dev, sp, out_idx, out_dist, st);
+    if (rc) return rc;
+    int capp = nabo_next_pow2(sp.nsplit * ksel);
+    if (capp < 32) capp = 32;
+    const size_t smem = (size_t)4 * capp * (sizeof(double) + sizeof(int));
+    NABO_CUDA(cudaFuncSetAttribute(fallback_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fallback_merge_kernel<<<(NABO_FALLBACK_SPLIT_ROWS + 3) / 4, 128, smem, st>>>(sp, row_ids, n_rows_dev, k, drop_first,
+                                                                               idx_offset, mask, capp, out_idx, out_dist);
+    NABO_LAUNCH_CHECK("fallback_merge_kernel");
+    sp.mode = 2;
+    return nabo_knn_exact_launch_ex(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
+                                    row_ids, n_rows_dev, sp, out_idx, out_dist, st);
+}
+
 int nabo_knn_exact_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
                           int k, int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                           const int* row_ids, const int* n_rows_dev, int32_t* out_idx, double* out_dist,
                           cudaStream_t st) {
+    NaboExactSplit sp;
+    sp.mode = 0; sp.nsplit = 1; sp.f_max = 0; sp.part_idx = nullptr; sp.part_dist = nullptr;
+    return nabo_knn_exact_launch_ex(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
+                                    row_ids, n_rows_dev, sp, out_idx, out_dist, st);
+}
+
+int nabo_knn_exact_launch_ex(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
+                             int k, int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
+                             const int* row_ids, const int* n_rows_dev, const NaboExactSplit& sp, int32_t* out_idx,
+                             double* out_dist, cudaStream_t st) {
     const int ksel = k + (drop_first ? 1 : 0);
     NABO_ARG(k >= 1 && ksel <= 128, "knn: k=%d unsupported (1 <= k, k + drop_first <= 128)", k);
     NABO_ARG(g >= 1, "knn: g=%d", g);
@@ -366,11 +481,11 @@ int nabo_knn_exact_launch(const double* q, int ldq, const double* r, int ldr, in
     const int cap = exact_cap_for(ksel);
     size_t smem = exact_smem_bytes(g, cap);
     NABO_ARG(smem <= 227 * 1024, "knn: g=%d with k=%d needs %zu B of shared memory (max 232448)", g, k, smem);
-    dim3 grid((n_query + TQ - 1) / TQ);
+    dim3 grid((n_query + TQ - 1) / TQ, sp.mode == 1 ? sp.nsplit : 1);
 #define LAUNCH(M)                                                                                         \
     NABO_CUDA(cudaFuncSetAttribute(knn_exact_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     knn_exact_kernel<M><<<grid, NT, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, \
-                                                idx_offset, row_ids, n_rows_dev, cap, out_idx, out_dist);
+                                                idx_offset, row_ids, n_rows_dev, cap, sp, out_idx, out_dist);
     if (metric == NABO_EUCLIDEAN) { LAUNCH(NABO_EUCLIDEAN) }
     else if (metric == NABO_MOD_CANBERRA) { LAUNCH(NABO_MOD_CANBERRA) }
     else if (metric == NABO_COSINE) { LAUNCH(NABO_COSINE) }

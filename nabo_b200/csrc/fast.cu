@@ -12,8 +12,10 @@ static const double kCAcc = 1.52587890625e-05;   // 2^-16
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric) {
     if (metric == NABO_MOD_CANBERRA)
         return nabo_align_up((size_t)n_query * nabo_cb_kprime(k, 1) * 4, 256) + 3 * nabo_align_up((size_t)n_query * 4, 256) +
-               nabo_align_up(nabo_cb_pretile_floats(n_query, g) * 4, 256) + nabo_align_up(nabo_cb_pretile_floats(n_ref, g) * 4, 256) + 4096;
-    return nabo_tc_workspace_bytes(n_query, n_ref, g, k, 1) + nabo_align_up((size_t)n_query * 4, 256) + 1024;
+               nabo_align_up(nabo_cb_pretile_floats(n_query, g) * 4, 256) + nabo_align_up(nabo_cb_pretile_floats(n_ref, g) * 4, 256) +
+               nabo_align_up(nabo_exact_split_workspace(k + 1), 256) + 4096;
+    return nabo_tc_workspace_bytes(n_query, n_ref, g, k, 1) + nabo_align_up((size_t)n_query * 4, 256) +
+           nabo_align_up(nabo_exact_split_workspace(k + 1), 256) + 1024;
 }
 
 int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
@@ -37,6 +39,7 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
         int* fail_count = ar.take<int>(1);
         float* qt = ar.take<float>(nabo_cb_pretile_floats(n_query, g));
         float* rt = ar.take<float>(nabo_cb_pretile_floats(n_ref, g));
+        char* split_ws = ar.take<char>(nabo_exact_split_workspace(k + (drop_first ? 1 : 0)));
         if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
         NABO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
         int rc = nabo_cb_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, qt, rt, cand, tau, st);
@@ -48,15 +51,15 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
                                 kprime, cert, fail_rows, fail_count, out_idx, out_dist, st);
         if (rc) return rc;
         tm.end(1);
-        rc = nabo_knn_exact_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
-                                   fail_rows, fail_count, out_idx, out_dist, st);
+        rc = nabo_knn_exact_fallback(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
+                                     fail_rows, fail_count, split_ws, out_idx, out_dist, st);
         if (rc) return rc;
         tm.end(2);
         if (stats_host) {
             int nfail = 0;
             NABO_CUDA(cudaMemcpyAsync(&nfail, fail_count, sizeof(int), cudaMemcpyDeviceToHost, st));
             NABO_CUDA(cudaStreamSynchronize(st));
-            stats_host[0] = n_query; stats_host[1] = nfail; stats_host[2] = kprime; stats_host[3] = 5;
+            stats_host[0] = n_query; stats_host[1] = nfail; stats_host[2] = kprime; stats_host[3] = 7;
             stats_host[4] = tm.ns(0); stats_host[5] = tm.ns(1); stats_host[6] = tm.ns(2);
         }
         return 0;
@@ -87,6 +90,7 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
     if (rc) return rc;
     int* fail_rows = ar.take<int>(n_query);
     int* fail_count = ar.take<int>(1);
+    char* split_ws = ar.take<char>(nabo_exact_split_workspace(k + (drop_first ? 1 : 0)));
     if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
     NABO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
     NaboCert cert;
@@ -98,8 +102,8 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
     tm.end(1);
     // rows the certificate did not clear: exact brute force (grid sized for the worst case,
     // blocks beyond the device-side row count exit immediately)
-    rc = nabo_knn_exact_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
-                               fail_rows, fail_count, out_idx, out_dist, st);
+    rc = nabo_knn_exact_fallback(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
+                                 fail_rows, fail_count, split_ws, out_idx, out_dist, st);
     if (rc) return rc;
     tm.end(2);
     if (stats_host) {
@@ -109,7 +113,7 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
         stats_host[0] = n_query;
         stats_host[1] = nfail;
         stats_host[2] = kprime;
-        stats_host[3] = launches + 2;
+        stats_host[3] = launches + 4;
         stats_host[4] = tm.ns(0);
         stats_host[5] = tm.ns(1);
         stats_host[6] = tm.ns(2);

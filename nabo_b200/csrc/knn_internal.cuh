@@ -2,6 +2,27 @@
 #pragma once
 #include "common.cuh"
 
+// Split fallback: with at most NABO_FALLBACK_SPLIT_ROWS uncertified rows the exact engine splits the
+// reference range over blockIdx.y and merges the partial lists (a single block would otherwise scan
+// the whole reference alone and dominate the call).
+#define NABO_FALLBACK_SPLIT_ROWS 2048
+struct NaboExactSplit {
+    int mode;            // 0 = plain, 1 = split partial pass (runs iff rows <= f_max), 2 = plain iff rows > f_max
+    int nsplit, f_max;
+    int32_t* part_idx;   // [nsplit][f_max][ksel]
+    double* part_dist;
+};
+int nabo_exact_split_count(int ksel);
+size_t nabo_exact_split_workspace(int ksel);
+int nabo_knn_exact_launch_ex(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
+                             int k, int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
+                             const int* row_ids, const int* n_rows_dev, const NaboExactSplit& sp, int32_t* out_idx,
+                             double* out_dist, cudaStream_t st);
+int nabo_knn_exact_fallback(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
+                            int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
+                            const int* row_ids, const int* n_rows_dev, void* split_ws, int32_t* out_idx,
+                            double* out_dist, cudaStream_t st);
+
 int nabo_knn_exact_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
                           int k, int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                           const int* row_ids, const int* n_rows_dev, int32_t* out_idx, double* out_dist,

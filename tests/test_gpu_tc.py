@@ -112,3 +112,23 @@ def test_tc_score_error_bound(core):
         worst = max(worst, float(rel.max()))
     print("max tensor-core score error / bound term = %.3e (certificate constant 2^-16 = %.3e)" % (worst, 2.0 ** -16))
     assert worst < 2.0 ** -18
+
+
+@pytest.mark.parametrize("n_bad", [5, 700, 3000])
+def test_fallback_paths(core, n_bad):
+    """Uncertified rows: few -> reference-split exact pass + merge; many (> 2048) -> row-parallel exact pass."""
+    from nabo_b200 import synth
+    q = synth.pc_mixture(4000, 25, seed=101)
+    r = synth.pc_mixture(9000, 25, seed=1)
+    r[100:160] = r[100]                                   # 60 identical references
+    bad = np.random.default_rng(1).choice(4000, n_bad, replace=False)
+    q[bad] = r[100]                                       # ... that are the nearest cells of these queries: ties > K'
+    q[bad[: n_bad // 2], 3] = np.nan                      # and NaN rows
+    for kw in (dict(), dict(drop_first=True), dict(idx_offset=77)):
+        fi, fd, st = core.knn(q, r, 20, "euclidean", mode="fast", return_stats=True, **kw)
+        ei, ed = core.knn(q, r, 20, "euclidean", mode="exact", **kw)
+        assert st["rows_exact_fallback"] >= n_bad
+        assert same_bits(fd, ed) and np.array_equal(fi, ei)
+    fi, fd, st = core.knn(q, r, 20, "mod_canberra", 0.25, mode="fast", return_stats=True)
+    ei, ed = core.knn(q, r, 20, "mod_canberra", 0.25, mode="exact")
+    assert same_bits(fd, ed) and np.array_equal(fi, ei)
