@@ -19,7 +19,7 @@ from ._lib import METRICS, MODE_EXACT, MODE_FAST, check, lib, require_device
 
 __all__ = ["euclidean_dist", "mod_canberra_dist", "cosine_dist", "knn", "knn_candidates", "rerank_exact", "merge_topk",
            "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets",
-           "project", "project_csr", "scale_counts", "map_cells", "resolve_metric"]
+           "project", "project_csr", "scale_counts", "map_cells", "map_cells_host", "resolve_metric"]
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -126,7 +126,7 @@ def cosine_dist(x, y, d=None):
 
 # ----------------------------------------------------------------------------- (2) kNN
 def knn(q, r, k: int, metric: str = "euclidean", dist_factor: float = 0.25, ref_mask=None,
-        drop_first: bool = False, idx_offset: int = 0, mode: str = "fast", return_stats: bool = False):
+        drop_first: bool = False, idx_offset: int = 0, mode: str = "fast", return_stats: bool = False, out=None):
     """Fused distance + per-query top-k: what ``_calc_dist`` (nabo/_mapping.py:48-148) leaves
     for ``_calc_snn`` to read (``[:k]`` of each sorted row), without the N x M matrix.
 
@@ -150,8 +150,14 @@ def knn(q, r, k: int, metric: str = "euclidean", dist_factor: float = 0.25, ref_
     md = _mask_dev(ref_mask)
     if md is not None and md.numel() != m:
         raise ValueError("ERROR: ref_mask must have one entry per reference cell")
-    idx = torch.empty((n, k), dtype=torch.int32, device=qd.device)
-    dst = torch.empty((n, k), dtype=torch.float64, device=qd.device)
+    if out is not None:                                    # caller-owned (n, k) int32 / float64 device buffers
+        idx, dst = out
+        if tuple(idx.shape) != (n, k) or tuple(dst.shape) != (n, k) or idx.dtype != torch.int32 or \
+                dst.dtype != torch.float64 or not (idx.is_contiguous() and dst.is_contiguous() and idx.is_cuda):
+            raise ValueError("ERROR: out must be contiguous CUDA (n, k) int32 and float64 tensors")
+    else:
+        idx = torch.empty((n, k), dtype=torch.int32, device=qd.device)
+        dst = torch.empty((n, k), dtype=torch.float64, device=qd.device)
     mode_i = MODE_FAST if mode == "fast" else MODE_EXACT
     L = lib()
     ws_bytes = int(L.nabo_knn_workspace_bytes(n, m, g, k, METRICS[metric], mode_i))
@@ -244,7 +250,7 @@ def fix_weight(k: int) -> float:
     return 0.5 / ((2 * (k - 1)) - 0.5)
 
 
-def snn_weights(tgt_knn, ref_knn, k: Optional[int] = None):
+def snn_weights(tgt_knn, ref_knn, k: Optional[int] = None, out=None):
     """``_calc_snn`` (nabo/_mapping.py:151-200) in array form.
     Returns (counts uint8 (N,k), weights float64 (N,k)); an edge exists where counts > 0."""
     require_device()
@@ -256,8 +262,11 @@ def snn_weights(tgt_knn, ref_knn, k: Optional[int] = None):
     if k != kk:
         td = td[:, :k].contiguous()
     lut = _dev(snn_weight_lut(k), torch.float64)
-    cnt = torch.empty((n, k), dtype=torch.uint8, device=td.device)
-    w = torch.empty((n, k), dtype=torch.float64, device=td.device)
+    if out is not None:
+        cnt, w = out
+    else:
+        cnt = torch.empty((n, k), dtype=torch.uint8, device=td.device)
+        w = torch.empty((n, k), dtype=torch.float64, device=td.device)
     check(lib().nabo_snn_weights(_ptr(td), n, k, _ptr(rd), rd.shape[0], rd.shape[1], _ptr(lut), _ptr(cnt),
                                  _ptr(w), C.c_void_p(_stream())), "snn_weights")
     return _out(cnt, host), _out(w, host)
@@ -407,3 +416,70 @@ def map_cells(target, ref, ref_knn, k: int, metric: Optional[str] = None, dist_f
     if host:
         res = {k_: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k_, v in res.items()}
     return res
+
+
+class _HostPipeline:
+    """Reusable device / pinned-host buffers and streams of ``map_cells_host`` for one shape."""
+
+    def __init__(self, n, g, k, m, device):
+        self.key = (n, g, k, m, str(device))
+        self.dev_in = torch.empty((n, g), dtype=torch.float64, device=device)
+        self.idx = torch.empty((n, k), dtype=torch.int32, device=device)
+        self.dist = torch.empty((n, k), dtype=torch.float64, device=device)
+        self.cnt = torch.empty((n, k), dtype=torch.uint8, device=device)
+        self.w = torch.empty((n, k), dtype=torch.float64, device=device)
+        self.host = {"idx": torch.empty((n, k), dtype=torch.int32, pin_memory=True),
+                     "dist": torch.empty((n, k), dtype=torch.float64, pin_memory=True),
+                     "weights": torch.empty((n, k), dtype=torch.float64, pin_memory=True),
+                     "scores": torch.empty(m, dtype=torch.float64, pin_memory=True)}
+        self.s_in, self.s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+
+_PIPE: Dict[tuple, _HostPipeline] = {}
+
+
+def map_cells_host(target_host: torch.Tensor, ref, ref_knn, k: int, metric: Optional[str] = None,
+                   dist_factor: float = 0.25, ref_mask=None, mode: str = "fast", chunks: int = 2) -> Dict[str, torch.Tensor]:
+    """Host-buffer form of ``map_cells``: ``target_host`` is a pinned CPU float64 (N, g) tensor; the results
+    land in pinned host tensors (idx, dist, weights, scores).  The targets are processed in ``chunks``
+    pieces so that the host->device copy of piece i+1 and the device->host copy of piece i-1 overlap the
+    kernels of piece i (three CUDA streams); the per-reference scores are one reduction over all pieces."""
+    require_device()
+    rd = _dev(ref, torch.float64)
+    rk = _dev(ref_knn, torch.int32)
+    n, g = target_host.shape
+    m = rd.shape[0]
+    key = (n, g, int(k), m, str(rd.device))
+    pipe = _PIPE.get(key)
+    if pipe is None:
+        _PIPE.clear()
+        pipe = _PIPE[key] = _HostPipeline(n, g, int(k), m, rd.device)
+    met = resolve_metric(metric, False)
+    comp = torch.cuda.current_stream()
+    chunks = max(1, min(int(chunks), n // 32768 if n >= 65536 else 1))
+    bounds = [n * i // chunks for i in range(chunks + 1)]
+    pipe.s_in.wait_stream(comp)
+    pipe.s_out.wait_stream(comp)
+    ready = []
+    for lo, hi in zip(bounds, bounds[1:]):
+        with torch.cuda.stream(pipe.s_in):
+            pipe.dev_in[lo:hi].copy_(target_host[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(pipe.s_in)
+        ready.append(ev)
+    for (lo, hi), ev in zip(zip(bounds, bounds[1:]), ready):
+        comp.wait_event(ev)
+        knn(pipe.dev_in[lo:hi], rd, k, met, dist_factor, ref_mask, False, 0, mode, out=(pipe.idx[lo:hi], pipe.dist[lo:hi]))
+        snn_weights(pipe.idx[lo:hi], rk, k, out=(pipe.cnt[lo:hi], pipe.w[lo:hi]))
+        done = torch.cuda.Event()
+        done.record(comp)
+        with torch.cuda.stream(pipe.s_out):
+            pipe.s_out.wait_event(done)
+            pipe.host["idx"][lo:hi].copy_(pipe.idx[lo:hi], non_blocking=True)
+            pipe.host["dist"][lo:hi].copy_(pipe.dist[lo:hi], non_blocking=True)
+            pipe.host["weights"][lo:hi].copy_(pipe.w[lo:hi], non_blocking=True)
+    sc = mapping_scores(pipe.idx, pipe.cnt, m, k)
+    pipe.host["scores"].copy_(sc, non_blocking=True)
+    comp.synchronize()
+    pipe.s_out.synchronize()
+    return pipe.host

@@ -286,3 +286,18 @@ def test_projection_missing_genes_and_oracle(core):
     exp = O.project(dense, sf, mu, sigma, comps, mean)
     got = core.project(counts, gi, sf, mu, sigma, comps, mean)
     np.testing.assert_allclose(got, exp, rtol=0, atol=1e-11 * np.abs(exp).max())
+
+
+def test_map_cells_host_pipeline_equals_device_path(core):
+    import torch
+    from nabo_b200 import synth
+    n, m, g, k = 70000, 20000, 20, 10
+    ref = torch.from_numpy(synth.pc_mixture(m, g, seed=1)).cuda()
+    tgt = synth.pc_mixture(n, g, seed=101)
+    rk, _ = core.knn(ref, ref, k, "euclidean", drop_first=True)
+    a = core.map_cells(torch.from_numpy(tgt).cuda(), ref, rk, k, metric="euclidean")
+    h = core.map_cells_host(torch.from_numpy(tgt).pin_memory(), ref, rk, k, metric="euclidean")
+    assert torch.equal(h["idx"], a["idx"].cpu()) and torch.equal(h["dist"], a["dist"].cpu())
+    assert torch.equal(h["weights"], a["weights"].cpu()) and torch.equal(h["scores"], a["scores"].cpu())
+    h2 = core.map_cells_host(torch.from_numpy(tgt).pin_memory(), ref, rk, k, metric="euclidean", chunks=1)
+    assert torch.equal(h2["scores"], a["scores"].cpu())
