@@ -24,7 +24,7 @@ constexpr int CAP = 128;                // candidate keys per query in shared me
 
 struct Smem {
     float *xs, *xt, *xa;                // [g][TQ]  x, f|x|(1+delta), |x|
-    float *ys, *ya;                     // [g][TR]  y, |y| + 0.01
+    float *ys0, *ys1;                   // [g][TR]  y, double-buffered (cp.async prefetch of the next tile)
     unsigned long long* keys;           // [TQ][CAP]
     float* tau;                         // [TQ]
     int* cnt;                           // [TQ]
@@ -39,8 +39,8 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int g) {
     s.xs = f; f += (size_t)g * TQ;
     s.xt = f; f += (size_t)g * TQ;
     s.xa = f; f += (size_t)g * TQ;
-    s.ys = f; f += (size_t)g * TR;
-    s.ya = f; f += (size_t)g * TR;
+    s.ys0 = f; f += (size_t)g * TR;
+    s.ys1 = f; f += (size_t)g * TR;
     s.tau = f; f += TQ;
     s.cnt = reinterpret_cast<int*>(f);
     s.nwork = s.cnt + TQ;
@@ -101,20 +101,30 @@ candidates_kernel(const float* __restrict__ qt, const float* __restrict__ rt, in
         }
     }
     if (threadIdx.x < TQ) { s.cnt[threadIdx.x] = 0; s.tau[threadIdx.x] = CUDART_INF_F; }
+    if (threadIdx.x < 2) s.nwork[threadIdx.x] = 0;
 
-    for (int r0 = 0; r0 < n_ref; r0 += TR) {
-        __syncthreads();
-        {
-            const float4* src = reinterpret_cast<const float4*>(rt + (size_t)(r0 / TR) * g * TR);
-            for (int e = threadIdx.x; e < nvec; e += NT) {
-                const float4 y = src[e];
-                reinterpret_cast<float4*>(s.ys)[e] = y;
-                reinterpret_cast<float4*>(s.ya)[e] =
-                    make_float4(fabsf(y.x) + 0.01f, fabsf(y.y) + 0.01f, fabsf(y.z) + 0.01f, fabsf(y.w) + 0.01f);
-            }
+    // reference tiles are double-buffered: tile j+1 streams in with cp.async while tile j is processed
+    auto prefetch = [&](int tile, float* dst) {
+        const float4* src = reinterpret_cast<const float4*>(rt + (size_t)tile * g * TR);
+        for (int e = threadIdx.x; e < nvec; e += NT) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float4*>(dst) + e);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + e) : "memory");
         }
-        if (threadIdx.x == 0) *s.nwork = 0;
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int n_tiles = (n_ref + TR - 1) / TR;
+    prefetch(0, s.ys0);
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const int r0 = tile * TR;
+        float* ys = (tile & 1) ? s.ys1 : s.ys0;
+        int* nwork = s.nwork + (tile & 1);                 // work-list counters alternate between tiles
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // tile landed; phase 2 of the previous tile finished
+        if (tile + 1 < n_tiles) prefetch(tile + 1, (tile & 1) ? s.ys0 : s.ys1);
+        // compaction of the previous tile's appends rides inside the phase-1 region (no extra barrier):
+        // phase 1 only reads tau, and a slightly stale tau is still a valid threshold
+        for (int ql = warp; ql < TQ; ql += NT / 32)
+            if (s.cnt[ql] > CAP - TR) compact(s, ql, kprime, lane);
         // ---- phase 1: unsaturated-dimension counts of a 2 x 4 micro tile (float counters: FSET + FADD)
         float c[2][4];
 #pragma unroll
@@ -125,7 +135,7 @@ candidates_kernel(const float* __restrict__ qt, const float* __restrict__ rt, in
         for (int k = 0; k < g; ++k) {
             const float2 xv = *reinterpret_cast<const float2*>(s.xs + k * TQ + tq * 2);
             const float2 tv = *reinterpret_cast<const float2*>(s.xt + k * TQ + tq * 2);
-            const float4 yv = *reinterpret_cast<const float4*>(s.ys + k * TR + tr * 4);
+            const float4 yv = *reinterpret_cast<const float4*>(ys + k * TR + tr * 4);
             const float xx[2] = {xv.x, xv.y}, tt[2] = {tv.x, tv.y};
             const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
@@ -143,21 +153,22 @@ candidates_kernel(const float* __restrict__ qt, const float* __restrict__ rt, in
                 const int rl = tr * 4 + b, j = r0 + rl;
                 if (j >= n_ref || (mask && mask[j])) continue;
                 if ((float)g - c[a][b] < tau) {                   // d >= g - count: bound still below tau
-                    const int pos = atomicAdd(s.nwork, 1);
+                    const int pos = atomicAdd(nwork, 1);
                     s.work[pos] = (unsigned short)((ql << 8) | rl);
                 }
             }
         }
         __syncthreads();
         // ---- phase 2: dense evaluation of the survivors
-        const int nw = *s.nwork;
+        const int nw = *nwork;
+        if (threadIdx.x == 0) s.nwork[(tile + 1) & 1] = 0;       // nobody touches the other counter until the next tile
         for (int w = threadIdx.x; w < nw; w += NT) {
             const int ql = s.work[w] >> 8, rl = s.work[w] & 255;
             float acc = 0.f;
             for (int k = 0; k < g; ++k) {
-                const float x = s.xs[k * TQ + ql], y = s.ys[k * TR + rl];
+                const float x = s.xs[k * TQ + ql], y = ys[k * TR + rl];
                 const float num = fabsf(x - y);
-                const float term = __fdividef(num, s.xa[k * TQ + ql] + s.ya[k * TR + rl]);
+                const float term = __fdividef(num, s.xa[k * TQ + ql] + (fabsf(y) + 0.01f));
                 acc += (num < s.xt[k * TQ + ql]) ? term : 1.0f;
             }
             if (acc < s.tau[ql]) {
@@ -166,9 +177,6 @@ candidates_kernel(const float* __restrict__ qt, const float* __restrict__ rt, in
                     ((unsigned long long)float_to_sortable(acc) << 32) | (unsigned)(r0 + rl);
             }
         }
-        __syncthreads();
-        for (int ql = warp; ql < TQ; ql += NT / 32)
-            if (s.cnt[ql] > CAP - TR) compact(s, ql, kprime, lane);
     }
     __syncthreads();
     for (int ql = warp; ql < TQ; ql += NT / 32) {
