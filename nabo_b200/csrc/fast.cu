@@ -13,7 +13,7 @@ size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metri
     if (metric == NABO_MOD_CANBERRA)
         return nabo_align_up((size_t)n_query * nabo_cb_kprime(k, 1) * 4, 256) + 3 * nabo_align_up((size_t)n_query * 4, 256) +
                nabo_align_up(nabo_cb_pretile_floats(n_query, g) * 4, 256) + nabo_align_up(nabo_cb_pretile_floats(n_ref, g) * 4, 256) +
-               nabo_align_up(nabo_exact_split_workspace(k + 1), 256) + 4096;
+               nabo_align_up(nabo_exact_split_workspace(k + 1), 256) + nabo_align_up(nabo_cb_extra_bytes(n_ref, g), 256) + 4096;
     return nabo_tc_workspace_bytes(n_query, n_ref, g, k, 1) + nabo_align_up((size_t)n_query * 4, 256) +
            nabo_align_up(nabo_exact_split_workspace(k + 1), 256) + 1024;
 }
@@ -40,9 +40,10 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
         float* qt = ar.take<float>(nabo_cb_pretile_floats(n_query, g));
         float* rt = ar.take<float>(nabo_cb_pretile_floats(n_ref, g));
         char* split_ws = ar.take<char>(nabo_exact_split_workspace(k + (drop_first ? 1 : 0)));
+        char* extra = ar.take<char>(nabo_cb_extra_bytes(n_ref, g));
         if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
         NABO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
-        int rc = nabo_cb_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, qt, rt, cand, tau, st);
+        int rc = nabo_cb_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, qt, rt, extra, cand, tau, st);
         if (rc) return rc;
         tm.end(0);
         NaboCert cert;
@@ -59,7 +60,7 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
             int nfail = 0;
             NABO_CUDA(cudaMemcpyAsync(&nfail, fail_count, sizeof(int), cudaMemcpyDeviceToHost, st));
             NABO_CUDA(cudaStreamSynchronize(st));
-            stats_host[0] = n_query; stats_host[1] = nfail; stats_host[2] = kprime; stats_host[3] = 7;
+            stats_host[0] = n_query; stats_host[1] = nfail; stats_host[2] = kprime; stats_host[3] = 11;
             stats_host[4] = tm.ns(0); stats_host[5] = tm.ns(1); stats_host[6] = tm.ns(2);
         }
         return 0;

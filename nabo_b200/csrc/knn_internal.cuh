@@ -59,9 +59,10 @@ bool nabo_cb_supported(int g, int k, int drop_first);
 int nabo_cb_kprime(int k, int drop_first);
 double nabo_cb_eps(int g);
 size_t nabo_cb_pretile_floats(int n, int g);
+size_t nabo_cb_extra_bytes(int n_ref, int g);
 int nabo_cb_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
-                       double f, const uint8_t* mask, int drop_first, float* qt, float* rt, int32_t* cand, float* tau,
-                       cudaStream_t st);
+                       double f, const uint8_t* mask, int drop_first, float* qt, float* rt, void* extra, int32_t* cand,
+                       float* tau, cudaStream_t st);
 
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric);
 int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,

@@ -132,3 +132,32 @@ def test_fallback_paths(core, n_bad):
     fi, fd, st = core.knn(q, r, 20, "mod_canberra", 0.25, mode="fast", return_stats=True)
     ei, ed = core.knn(q, r, 20, "mod_canberra", 0.25, mode="exact")
     assert same_bits(fd, ed) and np.array_equal(fi, ei)
+
+
+@pytest.mark.parametrize("f", [0.05, 0.25, 1.5])
+def test_canberra_threshold_adversarial(core, f):
+    """Modified Canberra fast path: phase 1 counts unsaturated dimensions in FP16 with a widened threshold and
+    phase 2 scores in FP32; both must stay LOWER bounds.  References are built so that, for their query, most
+    dimensions sit within 1e-3 .. 1e-7 (relative) of the saturation boundary |x-y| = f|x|, with column
+    magnitudes from 1e-6 to 1e5 and a few zeros / tiny values; a violated bound would drop a true neighbour."""
+    rng = np.random.default_rng(int(f * 100))
+    nq, per, g, k = 300, 12, 24, 10
+    mag = 10.0 ** rng.uniform(-6, 5, size=g)
+    q = rng.normal(size=(nq, g)) * mag
+    q[:, 3] *= 1e-3
+    q[rng.random((nq, g)) < 0.02] = 0.0
+    refs = []
+    for rep in range(per):
+        delta = rng.choice([1e-3, -1e-3, 1e-4, -1e-4, 1e-5, -1e-5, 1e-7, -1e-7, 0.0], size=(nq, g))
+        sign = rng.choice([-1.0, 1.0], size=(nq, g))
+        y = q * (1.0 + sign * f * (1.0 - delta))
+        far = rng.random((nq, g)) < 0.25 + 0.05 * rep           # some dimensions clearly saturated
+        y[far] = (q * 3.0 + mag[None, :])[far]
+        refs.append(y)
+    r = np.concatenate(refs + [rng.normal(size=(2000, g)) * mag])
+    r = r[rng.permutation(len(r))]
+    fi, fd, st = core.knn(q, r, k, "mod_canberra", f, mode="fast", return_stats=True)
+    ei, ed = core.knn(q, r, k, "mod_canberra", f, mode="exact")
+    assert same_bits(fd, ed) and np.array_equal(fi, ei)
+    oi, od = O.knn(q[:64], r, k, "mod_canberra", f)
+    assert same_bits(fd[:64], od) and np.array_equal(fi[:64], oi)
