@@ -232,16 +232,26 @@ candidates_kernel(const float* __restrict__ qt, const float* __restrict__ rt, co
         // ---- phase 2: dense evaluation of the survivors
         const int nw = *nwork;
         if (threadIdx.x == 0) s.nwork[(tile + 1) & 1] = 0;       // nobody touches the other counter until the next tile
-        for (int w = threadIdx.x; w < nw; w += NT) {
+        // four lanes per surviving pair (dimensions k = part, part + 4, ...), partial sums combined with two
+        // shuffles: the work list is short once tau is warm, and one thread per pair left most of the block
+        // idle at the next barrier.  (FP32 partial sums in a different order stay within nabo_cb_eps.)
+        for (int base = 0; base < nw * 4; base += NT) {
+            const int w4 = base + threadIdx.x;
+            const bool active = w4 < nw * 4;
+            const int w = active ? (w4 >> 2) : 0, part = w4 & 3;
             const int ql = s.work[w] >> 8, rl = s.work[w] & 255;
             float acc = 0.f;
-            for (int k = 0; k < g; ++k) {
-                const float x = s.xs[k * TQ + ql], y = ys[k * TR + rl];
-                const float num = fabsf(x - y);
-                const float term = __fdividef(num, s.xa[k * TQ + ql] + (fabsf(y) + 0.01f));
-                acc += (num < s.xt[k * TQ + ql]) ? term : 1.0f;
+            if (active) {
+                for (int k = part; k < g; k += 4) {
+                    const float x = s.xs[k * TQ + ql], y = ys[k * TR + rl];
+                    const float num = fabsf(x - y);
+                    const float term = __fdividef(num, s.xa[k * TQ + ql] + (fabsf(y) + 0.01f));
+                    acc += (num < s.xt[k * TQ + ql]) ? term : 1.0f;
+                }
             }
-            if (acc < s.tau[ql]) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (active && part == 0 && acc < s.tau[ql]) {
                 const int pos = atomicAdd(&s.cnt[ql], 1);
                 s.keys[(size_t)ql * CAP + pos] =
                     ((unsigned long long)float_to_sortable(acc) << 32) | (unsigned)(r0 + rl);
@@ -277,6 +287,12 @@ int nabo_cb_kprime(int k, int drop_first) {
 }
 
 size_t nabo_cb_pretile_floats(int n, int g) { return (size_t)((n + 63) / 64) * g * 64; }
+int nabo_cb_pretile_launch(const double* x, int ld, int n, int g, float* out, cudaStream_t st) {
+    const size_t t = nabo_cb_pretile_floats(n, g);
+    cb::pretile_kernel<<<(unsigned)((t + 255) / 256), 256, 0, st>>>(x, ld, n, g, out);
+    NABO_LAUNCH_CHECK("cb::pretile_kernel");
+    return 0;
+}
 // extra workspace of the FP16 phase: half tiles of the reference + per-dimension max / scale
 size_t nabo_cb_extra_bytes(int n_ref, int g) {
     return nabo_align_up(nabo_cb_pretile_floats(n_ref, g) * 2, 256) + 2 * nabo_align_up((size_t)g * 4, 256) + 512;
@@ -327,4 +343,4 @@ int nabo_cb_candidates(const double* q, int ldq, const double* r, int ldr, int n
 
 // |FP32 score - (a lower bound of) the exact distance|: sequential FP32 sum of g terms <= 1 plus the
 // per-term rounding of the difference, the denominator and the approximate division.
-double nabo_cb_eps(int g) { return 1.2e-7 * (double)g * g + 2e-6 * g; }
+double nabo_cb_eps(int g) { return 1.2e-7 * (double)g * g + 2e-6 * g + 4e-7 * g; }

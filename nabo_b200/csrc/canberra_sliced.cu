@@ -1,0 +1,563 @@
+// Bit-sliced candidate pass for the modified Canberra metric (nabo/_mapping.py:29-45).
+//
+// d(x, y) = sum_k term_k with term_k = 1 unless |x_k - y_k| < f|x_k| ("unsaturated"), so
+// d >= g - count(x, y), count = number of unsaturated dimensions.  A pair whose bound reaches the
+// query's running threshold tau cannot enter the top-K' and needs no arithmetic at all.  This kernel
+// evaluates an OVER-estimate of count for 32 references per machine word:
+//
+//   * every dimension is cut into NBINS value bins (edges = sample quantiles of the reference); a
+//     reference word stores, per dimension, the cumulative bit planes P[p] = [bin(y) < p], p = 0..NBINS;
+//   * the unsaturated y of a query form the interval (x - f|x|, x + f|x|); with lo / hi the bins of its
+//     (outward rounded) end points, P[hi + 1] & ~P[lo] flags every reference whose bin meets the interval -
+//     a superset of the unsaturated ones, for 32 references with two shared-memory loads and one LOP3;
+//   * the g flag words are summed vertically with a carry-save adder tree (Harley-Seal, 2.25 LOP3 per
+//     dimension) into a 6-bit sliced counter and compared with need(tau) = min{c : g - c < tau};
+//   * the surviving pairs (about 2 % once tau is warm) go through the dense FP32 evaluation
+//     (same arithmetic and error bound nabo_cb_eps as canberra_candidates.cu) and the running top-K'
+//     selection of select.cuh.
+//
+// Lanes are queries: a warp owns 32 queries for the whole reference sweep (their bin intervals live in
+// registers, their thresholds / counts in a private shared-memory slice), the NW consumer warps of a CTA
+// share the reference tiles that one producer warp streams in with TMA bulk copies through an mbarrier
+// ring - no CTA-wide barrier in the sweep.  Everything rejected has exact distance >= tau - eps, which
+// is what the re-rank certificate (NABO_CERT_LINEAR) needs; results are identical to the exact engine.
+#include "common.cuh"
+#include "knn_internal.cuh"
+#include "ptx.cuh"
+#include "select.cuh"
+
+#include <stdlib.h>
+
+namespace cbs {
+
+using namespace sel;   // make_key, compact_select, compact_sort_inline
+
+constexpr int NBINS = 16;                 // value bins per dimension
+constexpr int NPL = NBINS + 1;            // cumulative planes per (dimension, word)
+constexpr int RT = 128;                   // references per tile
+constexpr int WPT = RT / 32;              // words per tile
+constexpr int NW = 12;                    // consumer warps per CTA
+constexpr int QB = NW * 32;               // queries per work item
+constexpr int NTHREADS = (NW + 1) * 32;   // + producer warp
+constexpr int LC = 512;                   // work-list entries per warp
+constexpr int CAP = sel::CAP;
+constexpr int MAX_STAGES = 4;
+constexpr int EDGE_SAMPLE = 4096;
+
+static inline int nblocks8(int g) { return (g + 7) / 8; }
+static inline size_t plane_tile_bytes(int g) { return (size_t)g * WPT * NPL * 4; }
+static inline size_t ys_tile_bytes(int g) { return (size_t)g * RT * 4; }
+
+struct SmemPlan {
+    int stages;
+    size_t stage_bytes, stage_off, xs_off, hist_off, work_off, tau_off, cnt_off, bar_off, total;
+};
+static SmemPlan plan_smem(int g) {
+    SmemPlan p;
+    p.stage_bytes = plane_tile_bytes(g) + ys_tile_bytes(g);
+    const size_t fixed = (size_t)NW * g * 32 * 4 + (size_t)NW * 256 * 4 + (size_t)NW * LC * 2 + (size_t)NW * 32 * 8 + 128;
+    const size_t cap = 227 * 1024;
+    p.stages = 0;
+    for (int s = MAX_STAGES; s >= 2; --s)
+        if (fixed + s * p.stage_bytes <= cap) { p.stages = s; break; }
+    size_t o = 0;
+    p.stage_off = o; o += (size_t)(p.stages > 0 ? p.stages : 2) * p.stage_bytes;
+    p.xs_off = o; o += (size_t)NW * g * 32 * 4;
+    p.hist_off = o; o += (size_t)NW * 256 * 4;
+    p.work_off = o; o += (size_t)NW * LC * 2;
+    p.tau_off = o; o += (size_t)NW * 32 * 4;
+    p.cnt_off = o; o += (size_t)NW * 32 * 4;
+    p.bar_off = o; o += 128;
+    p.total = o;
+    return p;
+}
+
+// ------------------------------------------------------------------ preparation kernels
+// Bin edges of one dimension: NBINS-quantiles of a strided sample of the reference (any edges are valid,
+// quantiles just make the bins equally selective).  edges[k][j], j < NBINS - 1, ascending.
+__global__ void __launch_bounds__(1024)
+edges_kernel(const double* __restrict__ r, int ld, int n_ref, float* __restrict__ edges) {
+    __shared__ float v[EDGE_SAMPLE];
+    const int k = blockIdx.x;
+    const int ns = n_ref < EDGE_SAMPLE ? n_ref : EDGE_SAMPLE;
+    for (int i = threadIdx.x; i < EDGE_SAMPLE; i += blockDim.x) {
+        float x = CUDART_INF_F;
+        if (i < ns) {
+            const long long row = (long long)i * n_ref / ns;
+            x = (float)r[row * ld + k];
+            if (!(x == x)) x = CUDART_INF_F;
+        }
+        v[i] = x;
+    }
+    __syncthreads();
+    for (int size = 2; size <= EDGE_SAMPLE; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < EDGE_SAMPLE / 2; t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const float a = v[lo], b = v[hi];
+                if (up ? (b < a) : (a < b)) { v[lo] = b; v[hi] = a; }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x < NBINS - 1) {
+        int pos = (int)(((long long)(threadIdx.x + 1) * ns) / NBINS) - 1;
+        if (pos < 0) pos = 0;
+        edges[k * (NBINS - 1) + threadIdx.x] = v[pos];
+    }
+}
+
+__device__ __forceinline__ int bin_of(float y, const float* e) {
+    int b = 0;
+#pragma unroll
+    for (int j = 0; j < NBINS - 1; ++j) b += (e[j] <= y) ? 1 : 0;
+    return b;
+}
+
+// Cumulative planes of one (tile, dimension): planes[((tile * g + k) * WPT + w) * NPL + p], bit i of word w
+// = reference tile * RT + w * 32 + i is live (in range, not masked) and bin(y) < p.  rt is the FP32
+// pre-tiled reference of canberra_candidates.cu ([tile64][k][64]).
+__global__ void __launch_bounds__(RT)
+planes_kernel(const float* __restrict__ rt, const float* __restrict__ edges, const uint8_t* __restrict__ mask,
+              int n_ref, int g, uint32_t* __restrict__ planes) {
+    __shared__ float e[NBINS - 1];
+    const int tile = blockIdx.x, k = blockIdx.y;
+    if (threadIdx.x < NBINS - 1) e[threadIdx.x] = edges[k * (NBINS - 1) + threadIdx.x];
+    __syncthreads();
+    const int ref = tile * RT + threadIdx.x;
+    const bool live = ref < n_ref && !(mask && mask[ref]);
+    const float y = live ? rt[((size_t)(ref >> 6) * g + k) * 64 + (ref & 63)] : 0.f;
+    const int b = bin_of(y, e);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, live && b < p);
+        if (lane == p) mine = bits;
+    }
+    if (lane < NPL) planes[(((size_t)tile * g + k) * WPT + w) * NPL + lane] = mine;
+}
+
+// Per (query, dimension) plane byte offsets: low byte = 4 * lo, high byte = 4 * (hi + 1), 0 / 0 for an empty
+// interval (x = 0 or NaN: nothing is unsaturated).  Two dimensions per 32-bit word, lanes interleaved:
+// ctrl[(group32 * nj + j) * 32 + lane].  The interval is widened by 1e-6 relative (FP64 rounding of the
+// reference's own test) and its end points are rounded outward to FP32 - the precision the planes were
+// binned in; float rounding is monotone, so bin(y) of every unsaturated y lies in [lo, hi].
+__global__ void __launch_bounds__(256)
+ctrl_kernel(const double* __restrict__ q, int ld, int n_query, int g, int nj, double f,
+            const float* __restrict__ edges, uint32_t* __restrict__ ctrl, long long total) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int lane = (int)(e & 31);
+    const long long gj = e >> 5;
+    const int j = (int)(gj % nj);
+    const long long row = (gj / nj) * 32 + lane;
+    uint32_t word = 0;
+    for (int h = 0; h < 2; ++h) {
+        const int k = 2 * j + h;
+        uint32_t c = 0;
+        if (row < n_query && k < g) {
+            const double x = q[row * ld + k];
+            const double t = f * fabs(x) * (1.0 + 1e-6);
+            if (t > 0.0) {
+                const float lo_v = __double2float_rd(x - t), hi_v = __double2float_ru(x + t);
+                const float* ed = edges + k * (NBINS - 1);
+                int lo = 0, hi = 0;
+                for (int i = 0; i < NBINS - 1; ++i) {
+                    const float ev = ed[i];
+                    lo += (ev <= lo_v) ? 1 : 0;
+                    hi += (ev <= hi_v) ? 1 : 0;
+                }
+                if (!(hi_v == hi_v)) hi = NBINS - 1;      // x + t overflowed to NaN / inf: keep everything
+                if (!(lo_v == lo_v)) lo = 0;
+                c = (uint32_t)(lo * 4) | ((uint32_t)((hi + 1) * 4) << 8);
+            }
+        }
+        word |= c << (16 * h);
+    }
+    ctrl[e] = word;
+}
+
+// FP32 queries, 32 per group, dimension-major: qx[(group32 * g + k) * 32 + lane]
+__global__ void __launch_bounds__(256)
+pretile32_kernel(const double* __restrict__ x, int ld, int n, int g, float* __restrict__ out, long long total) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int lane = (int)(e & 31);
+    const long long gk = e >> 5;
+    const int k = (int)(gk % g);
+    const long long row = (gk / g) * 32 + lane;
+    out[e] = row < n ? (float)x[row * ld + k] : 0.f;
+}
+
+// ------------------------------------------------------------------ the sweep
+struct Params {
+    const uint32_t* planes;     // [n_tiles][g][WPT][NPL]
+    const float* rt;            // [n_tiles64][g][64]
+    const float* qx;            // [n_groups][g][32]
+    const uint32_t* ctrl;       // [n_groups][nj][32]
+    int n_query, n_ref, g, n_tiles, n_tiles64, n_items, kprime, stages, nj;
+    float fm;
+    unsigned long long* cand_buf;   // [gridDim][QB][CAP]
+    int32_t* cand;              // [n_query][kprime]
+    float* tau_out;             // [n_query]
+    size_t stage_bytes, stage_off, xs_off, hist_off, work_off, tau_off, cnt_off, bar_off;
+};
+
+struct Barriers {
+    uint64_t full[MAX_STAGES], empty[MAX_STAGES];
+};
+
+#define NABO_CSA(h, l, a, b, c)                           \
+    {                                                     \
+        const uint32_t u_ = (a) ^ (b);                    \
+        const uint32_t c_ = (c);                          \
+        h = ((a) & (b)) | (u_ & c_);                      \
+        l = u_ ^ c_;                                      \
+    }
+
+// smallest count c with (float)g - c < tau, clamped to [0, 63]
+__device__ __forceinline__ int need_of(float tau, int g) {
+    if (!(tau > -CUDART_INF_F)) return 63;
+    if (tau == CUDART_INF_F) return 0;
+    int c = (int)floorf((float)g - tau) + 1;
+    if (c < 0) c = 0;
+    while (c > 0 && (float)(g - (c - 1)) < tau) --c;
+    while (c < 63 && !((float)(g - c) < tau)) ++c;
+    return c > 63 ? 63 : c;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(NTHREADS, 1)
+sliced_kernel(const Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Barriers* bars = reinterpret_cast<Barriers*>(smem + p.bar_off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = p.g;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&bars->full[s], 1); ptx::mbar_init(&bars->empty[s], NW); }
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+
+    const uint32_t plane_bytes = (uint32_t)((size_t)g * WPT * NPL * 4);
+    if (warp == NW) {
+        // ===================== producer: one lane streams the reference tiles =====================
+        if (lane == 0) {
+            uint32_t t = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                for (int j = 0; j < p.n_tiles; ++j, ++t) {
+                    const uint32_t s = t % p.stages, use = t / p.stages;
+                    ptx::mbar_wait(&bars->empty[s], (use & 1) ^ 1);
+                    const int n64 = min(2, p.n_tiles64 - 2 * j);
+                    const uint32_t ys_bytes = (uint32_t)n64 * g * 64 * 4;
+                    ptx::mbar_arrive_expect_tx(&bars->full[s], plane_bytes + ys_bytes);
+                    char* dst = reinterpret_cast<char*>(smem + p.stage_off + (size_t)s * p.stage_bytes);
+                    const char* src = reinterpret_cast<const char*>(p.planes) + (size_t)j * plane_bytes;
+                    for (uint32_t o = 0; o < plane_bytes; o += 16384)
+                        ptx::bulk_g2s(dst + o, src + o, min(16384u, plane_bytes - o), &bars->full[s]);
+                    dst += plane_bytes;
+                    src = reinterpret_cast<const char*>(p.rt) + (size_t)j * 2 * g * 64 * 4;
+                    for (uint32_t o = 0; o < ys_bytes; o += 16384)
+                        ptx::bulk_g2s(dst + o, src + o, min(16384u, ys_bytes - o), &bars->full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers: lanes = queries =====================
+    float* xs = reinterpret_cast<float*>(smem + p.xs_off) + (size_t)warp * g * 32;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem + p.hist_off) + (size_t)warp * 256;
+    unsigned short* work = reinterpret_cast<unsigned short*>(smem + p.work_off) + (size_t)warp * LC;
+    float* s_tau = reinterpret_cast<float*>(smem + p.tau_off) + warp * 32;
+    int* s_cnt = reinterpret_cast<int*>(smem + p.cnt_off) + warp * 32;
+    unsigned long long* gbuf = p.cand_buf + ((size_t)blockIdx.x * QB + warp * 32) * CAP;
+    const float fm = p.fm;
+    const int kprime = p.kprime;
+
+    // dense FP32 evaluation of the first n work-list entries of the current tile
+    auto evaluate = [&](int n, const float* ys, int ref0) {
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const bool active = i < n;
+            const int e = active ? work[i] : 0;
+            const int ql = e >> 8, rl = e & 127;
+            const float* xb = xs + ql;
+            const float* yb = ys + (rl >> 6) * (g * 64) + (rl & 63);
+            float acc = 0.f;
+#pragma unroll 5
+            for (int k = 0; k < g; ++k) {
+                const float x = xb[k * 32], y = yb[k * 64];
+                const float num = fabsf(x - y), xa = fabsf(x);
+                const float term = __fdividef(num, xa + (fabsf(y) + 0.01f));
+                acc += (num < fm * xa) ? term : 1.0f;
+            }
+            if (active && acc < s_tau[ql]) {
+                const int pos = atomicAdd(&s_cnt[ql], 1);
+                gbuf[(size_t)ql * CAP + pos] = make_key(acc, (uint32_t)(ref0 + rl));
+            }
+            __syncwarp();
+            // a round adds at most 32 keys to one query: keep every buffer at or below CAP - 32
+            unsigned need = __ballot_sync(0xffffffffu, s_cnt[lane] > CAP - 32);
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                int nc;
+                float nt;
+                compact_select(gbuf + (size_t)src * CAP, s_cnt[src], lane, kprime, CAP - 40, hist, nc, nt);
+                if (lane == src) { s_cnt[lane] = nc; s_tau[lane] = nt; }
+                __syncwarp();
+            }
+        }
+    };
+
+    uint32_t t = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int group = item * NW + warp;
+        const long long q_mine = (long long)group * 32 + lane;
+        uint32_t ctrl[NB * 4];
+#pragma unroll
+        for (int j = 0; j < NB * 4; ++j) ctrl[j] = p.ctrl[((size_t)group * p.nj + j) * 32 + lane];
+        for (int e = lane; e < g * 32; e += 32) xs[e] = p.qx[(size_t)group * g * 32 + e];
+        s_tau[lane] = q_mine < p.n_query ? CUDART_INF_F : -CUDART_INF_F;     // padding queries reject everything
+        s_cnt[lane] = 0;
+        __syncwarp();
+
+        for (int j = 0; j < p.n_tiles; ++j, ++t) {
+            const uint32_t s = t % p.stages, use = t / p.stages;
+            ptx::mbar_wait(&bars->full[s], use & 1);
+            const unsigned char* stage = smem + p.stage_off + (size_t)s * p.stage_bytes;
+            const char* pl = reinterpret_cast<const char*>(stage);
+            const float* ys = reinterpret_cast<const float*>(stage + plane_bytes);
+
+            // ---- phase 0: sliced over-estimate of the unsaturated-dimension count, 4 x 32 references per lane
+            uint32_t c[WPT][6];
+#pragma unroll
+            for (int w = 0; w < WPT; ++w)
+#pragma unroll
+                for (int b = 0; b < 6; ++b) c[w][b] = 0u;
+#pragma unroll
+            for (int blk = 0; blk < NB; ++blk) {
+                uint32_t v[8][WPT];
+#pragma unroll
+                for (int d = 0; d < 8; ++d) {
+                    const int k = blk * 8 + d;
+                    if (blk < NB - 1 || k < g) {
+                        const uint32_t cw = ctrl[k >> 1];
+                        const uint32_t lo4 = (k & 1) ? ((cw >> 16) & 0xffu) : (cw & 0xffu);
+                        const uint32_t hi4 = (k & 1) ? (cw >> 24) : ((cw >> 8) & 0xffu);
+                        const char* base = pl + k * (WPT * NPL * 4);
+#pragma unroll
+                        for (int w = 0; w < WPT; ++w) {
+                            const uint32_t a = *reinterpret_cast<const uint32_t*>(base + w * NPL * 4 + hi4);
+                            const uint32_t b = *reinterpret_cast<const uint32_t*>(base + w * NPL * 4 + lo4);
+                            v[d][w] = a & ~b;
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < WPT; ++w) v[d][w] = 0u;
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < WPT; ++w) {
+                    uint32_t t2a, t2b, f4a, f4b, e8;
+                    NABO_CSA(t2a, c[w][0], c[w][0], v[0][w], v[1][w]);
+                    NABO_CSA(t2b, c[w][0], c[w][0], v[2][w], v[3][w]);
+                    NABO_CSA(f4a, c[w][1], c[w][1], t2a, t2b);
+                    NABO_CSA(t2a, c[w][0], c[w][0], v[4][w], v[5][w]);
+                    NABO_CSA(t2b, c[w][0], c[w][0], v[6][w], v[7][w]);
+                    NABO_CSA(f4b, c[w][1], c[w][1], t2a, t2b);
+                    NABO_CSA(e8, c[w][2], c[w][2], f4a, f4b);
+                    const uint32_t k1 = c[w][3] & e8;
+                    c[w][5] ^= c[w][4] & k1;
+                    c[w][4] ^= k1;
+                    c[w][3] ^= e8;
+                }
+            }
+            // count >= need(tau), per lane
+            const int need_c = need_of(s_tau[lane], g);
+            uint32_t m[WPT];
+#pragma unroll
+            for (int w = 0; w < WPT; ++w) {
+                uint32_t gt = 0u, eq = 0xffffffffu;
+#pragma unroll
+                for (int b = 5; b >= 0; --b) {
+                    const uint32_t nb = 0u - (uint32_t)((need_c >> b) & 1);
+                    gt |= eq & c[w][b] & ~nb;
+                    eq &= ~(c[w][b] ^ nb);
+                }
+                const uint32_t live = *reinterpret_cast<const uint32_t*>(pl + (w * NPL + NBINS) * 4);
+                m[w] = (gt | eq) & live;
+            }
+
+            // ---- survivors -> work list -> phase 2
+            int mine = 0;
+#pragma unroll
+            for (int w = 0; w < WPT; ++w) mine += __popc(m[w]);
+            const int total = __reduce_add_sync(0xffffffffu, mine);
+            if (total > 0) {
+                if (total <= LC) {
+                    int incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += u;
+                    }
+                    int pos = incl - mine;
+#pragma unroll
+                    for (int w = 0; w < WPT; ++w) {
+                        uint32_t mm = m[w];
+                        while (mm) {
+                            const int b = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            work[pos++] = (unsigned short)((lane << 8) | (w * 32 + b));
+                        }
+                    }
+                    __syncwarp();
+                    evaluate(total, ys, j * RT);
+                } else {
+                    // dense tile (cold threshold): one byte column of one word at a time, at most 256 entries
+                    for (int w = 0; w < WPT; ++w) {
+                        for (int bg = 0; bg < 4; ++bg) {
+                            uint32_t mm = 0;
+#pragma unroll
+                            for (int ww = 0; ww < WPT; ++ww)
+                                if (ww == w) mm = m[ww];
+                            mm &= 0xffu << (8 * bg);
+                            const int cntl = __popc(mm);
+                            const int tot = __reduce_add_sync(0xffffffffu, cntl);
+                            if (tot == 0) continue;
+                            int incl = cntl;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                                if (lane >= o) incl += u;
+                            }
+                            int pos = incl - cntl;
+                            while (mm) {
+                                const int b = __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                work[pos++] = (unsigned short)((lane << 8) | (w * 32 + b));
+                            }
+                            __syncwarp();
+                            evaluate(tot, ys, j * RT);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars->empty[s]);
+        }
+
+        // ---- item done: exact selection of every query of this warp, emit candidates + threshold
+        for (int src = 0; src < 32; ++src) {
+            const int n = s_cnt[src];
+            const float old_tau = s_tau[src];
+            uint32_t ks[4], kpl[4];
+            int nc;
+            float nt;
+            compact_sort_inline(gbuf + (size_t)src * CAP, n, lane, kprime, ks, kpl, nc, nt);
+            const long long qg = (long long)group * 32 + src;
+            if (qg < p.n_query) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = u * 32 + lane;
+                    if (i < kprime) p.cand[qg * kprime + i] = i < nc ? (int32_t)kpl[u] : -1;
+                }
+                if (lane == 0) p.tau_out[qg] = n >= kprime ? nt : old_tau;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace cbs
+
+// ------------------------------------------------------------------ host side
+bool nabo_cbs_supported(int g, int k, int drop_first) {
+    const char* legacy = getenv("NABO_CB_LEGACY");
+    if (legacy && legacy[0] == '1') return false;
+    if (g < 1 || g > 64) return false;
+    const int ksel = k + (drop_first ? 1 : 0);
+    return cbs::plan_smem(g).stages >= 2 && ksel + 8 <= cbs::CAP - 64;
+}
+
+static int cbs_grid(int n_items) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return n_items < sms ? n_items : sms;
+}
+
+size_t nabo_cbs_extra_bytes(int n_query, int n_ref, int g) {
+    const size_t n_tiles = (n_ref + cbs::RT - 1) / cbs::RT;
+    const size_t n_groups = (size_t)((n_query + cbs::QB - 1) / cbs::QB) * cbs::NW;
+    const int nj = cbs::nblocks8(g) * 4;
+    size_t b = 0;
+    b += nabo_align_up(n_tiles * cbs::plane_tile_bytes(g), 256);
+    b += nabo_align_up((size_t)g * (cbs::NBINS - 1) * 4, 256);
+    b += nabo_align_up(n_groups * nj * 32 * 4, 256);
+    b += nabo_align_up(n_groups * g * 32 * 4, 256);
+    b += nabo_align_up((size_t)148 * cbs::QB * cbs::CAP * 8, 256);
+    return b + 1024;
+}
+
+// rt: FP32 pre-tiled reference ([tile64][k][64], nabo_cb_pretile_floats(n_ref, g) floats), filled here.
+int nabo_cbs_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
+                        double f, const uint8_t* mask, int drop_first, float* rt, void* extra, size_t extra_bytes,
+                        int32_t* cand, float* tau, cudaStream_t st) {
+    const int kprime = nabo_cb_kprime(k, drop_first);
+    const cbs::SmemPlan pl = cbs::plan_smem(g);
+    const int n_tiles = (n_ref + cbs::RT - 1) / cbs::RT;
+    const int n_tiles64 = (n_ref + 63) / 64;
+    const int n_items = (n_query + cbs::QB - 1) / cbs::QB;
+    const size_t n_groups = (size_t)n_items * cbs::NW;
+    const int nb = cbs::nblocks8(g), nj = nb * 4;
+    const int grid = cbs_grid(n_items);
+
+    NaboArena ar(extra, extra_bytes);
+    uint32_t* planes = (uint32_t*)ar.take<char>((size_t)n_tiles * cbs::plane_tile_bytes(g));
+    float* edges = ar.take<float>((size_t)g * (cbs::NBINS - 1));
+    uint32_t* ctrl = ar.take<uint32_t>(n_groups * nj * 32);
+    float* qx = ar.take<float>(n_groups * g * 32);
+    unsigned long long* cbuf = ar.take<unsigned long long>((size_t)grid * cbs::QB * cbs::CAP);
+    if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small for the sliced Canberra pass");
+
+    {
+        int rc = nabo_cb_pretile_launch(r, ldr, n_ref, g, rt, st);
+        if (rc) return rc;
+        cbs::edges_kernel<<<g, 1024, 0, st>>>(r, ldr, n_ref, edges);
+        cbs::planes_kernel<<<dim3(n_tiles, g), cbs::RT, 0, st>>>(rt, edges, mask, n_ref, g, planes);
+        const long long tc = (long long)n_groups * nj * 32;
+        cbs::ctrl_kernel<<<(unsigned)((tc + 255) / 256), 256, 0, st>>>(q, ldq, n_query, g, nj, f, edges, ctrl, tc);
+        const long long tq = (long long)n_groups * g * 32;
+        cbs::pretile32_kernel<<<(unsigned)((tq + 255) / 256), 256, 0, st>>>(q, ldq, n_query, g, qx, tq);
+        NABO_LAUNCH_CHECK("cbs preparation kernels");
+    }
+
+    cbs::Params p;
+    p.planes = planes; p.rt = rt; p.qx = qx; p.ctrl = ctrl;
+    p.n_query = n_query; p.n_ref = n_ref; p.g = g; p.n_tiles = n_tiles; p.n_tiles64 = n_tiles64;
+    p.n_items = n_items; p.kprime = kprime; p.stages = pl.stages; p.nj = nj;
+    const double delta = fmax(1e-5, 4e-7 * (2.0 + f) / f);      // same optimistic margin as canberra_candidates.cu
+    p.fm = (float)(f * (1.0 + delta));
+    p.cand_buf = cbuf; p.cand = cand; p.tau_out = tau;
+    p.stage_bytes = pl.stage_bytes; p.stage_off = pl.stage_off; p.xs_off = pl.xs_off; p.hist_off = pl.hist_off;
+    p.work_off = pl.work_off; p.tau_off = pl.tau_off; p.cnt_off = pl.cnt_off; p.bar_off = pl.bar_off;
+#define NABO_CBS_LAUNCH(NBV)                                                                                       \
+    case NBV:                                                                                                      \
+        NABO_CUDA(cudaFuncSetAttribute(cbs::sliced_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                       (int)pl.total));                                                            \
+        cbs::sliced_kernel<NBV><<<grid, cbs::NTHREADS, pl.total, st>>>(p);                                         \
+        break;
+    switch (nb) {
+        NABO_CBS_LAUNCH(1) NABO_CBS_LAUNCH(2) NABO_CBS_LAUNCH(3) NABO_CBS_LAUNCH(4)
+        NABO_CBS_LAUNCH(5) NABO_CBS_LAUNCH(6) NABO_CBS_LAUNCH(7) NABO_CBS_LAUNCH(8)
+        default: return nabo_set_error(NABO_EINVAL, "knn: sliced Canberra pass supports at most 64 dimensions");
+    }
+#undef NABO_CBS_LAUNCH
+    NABO_LAUNCH_CHECK("cbs::sliced_kernel");
+    return 0;
+}

@@ -9,11 +9,16 @@
 // measured on B200 by tests/test_gpu_tc.py::test_tc_score_error_bound, which asserts a >= 4x margin.
 static const double kCAcc = 1.52587890625e-05;   // 2^-16
 
+static size_t cb_extra_bytes(int n_query, int n_ref, int g) {
+    const size_t a = nabo_cb_extra_bytes(n_ref, g), b = nabo_cbs_extra_bytes(n_query, n_ref, g);
+    return a > b ? a : b;
+}
+
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric) {
     if (metric == NABO_MOD_CANBERRA)
         return nabo_align_up((size_t)n_query * nabo_cb_kprime(k, 1) * 4, 256) + 3 * nabo_align_up((size_t)n_query * 4, 256) +
                nabo_align_up(nabo_cb_pretile_floats(n_query, g) * 4, 256) + nabo_align_up(nabo_cb_pretile_floats(n_ref, g) * 4, 256) +
-               nabo_align_up(nabo_exact_split_workspace(k + 1), 256) + nabo_align_up(nabo_cb_extra_bytes(n_ref, g), 256) + 4096;
+               nabo_align_up(nabo_exact_split_workspace(k + 1), 256) + nabo_align_up(cb_extra_bytes(n_query, n_ref, g), 256) + 4096;
     return nabo_tc_workspace_bytes(n_query, n_ref, g, k, 1) + nabo_align_up((size_t)n_query * 4, 256) +
            nabo_align_up(nabo_exact_split_workspace(k + 1), 256) + 1024;
 }
@@ -40,10 +45,14 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
         float* qt = ar.take<float>(nabo_cb_pretile_floats(n_query, g));
         float* rt = ar.take<float>(nabo_cb_pretile_floats(n_ref, g));
         char* split_ws = ar.take<char>(nabo_exact_split_workspace(k + (drop_first ? 1 : 0)));
-        char* extra = ar.take<char>(nabo_cb_extra_bytes(n_ref, g));
+        char* extra = ar.take<char>(cb_extra_bytes(n_query, n_ref, g));
         if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
         NABO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
-        int rc = nabo_cb_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, qt, rt, extra, cand, tau, st);
+        int rc = nabo_cbs_supported(g, k, drop_first)
+                     ? nabo_cbs_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, rt, extra,
+                                           cb_extra_bytes(n_query, n_ref, g), cand, tau, st)
+                     : nabo_cb_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, qt, rt, extra, cand,
+                                          tau, st);
         if (rc) return rc;
         tm.end(0);
         NaboCert cert;

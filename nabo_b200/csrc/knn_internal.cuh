@@ -64,6 +64,14 @@ int nabo_cb_candidates(const double* q, int ldq, const double* r, int ldr, int n
                        double f, const uint8_t* mask, int drop_first, float* qt, float* rt, void* extra, int32_t* cand,
                        float* tau, cudaStream_t st);
 
+int nabo_cb_pretile_launch(const double* x, int ld, int n, int g, float* out, cudaStream_t st);
+// bit-sliced Canberra pass (canberra_sliced.cu); same outputs as nabo_cb_candidates
+bool nabo_cbs_supported(int g, int k, int drop_first);
+size_t nabo_cbs_extra_bytes(int n_query, int n_ref, int g);
+int nabo_cbs_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
+                        double f, const uint8_t* mask, int drop_first, float* rt, void* extra, size_t extra_bytes,
+                        int32_t* cand, float* tau, cudaStream_t st);
+
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric);
 int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                   int metric, double f, const uint8_t* mask, int drop_first, int idx_offset, int32_t* out_idx,
