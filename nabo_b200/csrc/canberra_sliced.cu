@@ -32,13 +32,13 @@ namespace cbs {
 
 using namespace sel;   // make_key, compact_select, compact_sort_inline
 
-constexpr int NBINS = 16;                 // value bins per dimension
+constexpr int NBINS = 32;                 // value bins per dimension
 constexpr int NPL = NBINS + 1;            // cumulative planes per (dimension, word)
 constexpr int RT = 128;                   // references per tile
 constexpr int WPT = RT / 32;              // words per tile
 constexpr int NW = 12;                    // consumer warps per CTA
-constexpr int QB = NW * 32;               // queries per work item
-constexpr int NTHREADS = (NW + 1) * 32;   // + producer warp
+constexpr int QB = NW * 32;               // queries a CTA handles per round (at most)
+constexpr int NTHREADS = NW * 32;
 constexpr int LC = 512;                   // work-list entries per warp
 constexpr int CAP = sel::CAP;
 constexpr int MAX_STAGES = 4;
@@ -129,13 +129,12 @@ planes_kernel(const float* __restrict__ rt, const float* __restrict__ edges, con
     const float y = live ? rt[((size_t)(ref >> 6) * g + k) * 64 + (ref & 63)] : 0.f;
     const int b = bin_of(y, e);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t mine = 0;
+    uint32_t* out = planes + (((size_t)tile * g + k) * WPT + w) * NPL;
 #pragma unroll
     for (int p = 0; p < NPL; ++p) {
         const uint32_t bits = __ballot_sync(0xffffffffu, live && b < p);
-        if (lane == p) mine = bits;
+        if (lane == (p & 31)) out[p] = bits;
     }
-    if (lane < NPL) planes[(((size_t)tile * g + k) * WPT + w) * NPL + lane] = mine;
 }
 
 // Per (query, dimension) plane byte offsets: low byte = 4 * lo, high byte = 4 * (hi + 1), 0 / 0 for an empty
@@ -196,7 +195,7 @@ struct Params {
     const float* rt;            // [n_tiles64][g][64]
     const float* qx;            // [n_groups][g][32]
     const uint32_t* ctrl;       // [n_groups][nj][32]
-    int n_query, n_ref, g, n_tiles, n_tiles64, n_items, kprime, stages, nj;
+    int n_query, n_ref, g, n_tiles, n_tiles64, n_groups, kprime, stages, nj;
     float fm;
     unsigned long long* cand_buf;   // [gridDim][QB][CAP]
     int32_t* cand;              // [n_query][kprime]
@@ -205,7 +204,8 @@ struct Params {
 };
 
 struct Barriers {
-    uint64_t full[MAX_STAGES], empty[MAX_STAGES];
+    uint64_t full[MAX_STAGES];
+    int done[MAX_STAGES];
 };
 
 #define NABO_CSA(h, l, a, b, c)                           \
@@ -235,37 +235,52 @@ sliced_kernel(const Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = p.g;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&bars->full[s], 1); ptx::mbar_init(&bars->empty[s], NW); }
-        ptx::fence_barrier_init();
-    }
-    __syncthreads();
+    // Work = 32-query groups, dealt evenly to the CTAs; a CTA sweeps the reference once per round with
+    // as many of its warps busy as it has groups left (balanced over the rounds).  Dealing whole
+    // NW-group items instead would leave most SMs idle whenever n_query / (32 NW) is not a multiple of the grid.
+    const int g_begin = (int)((long long)p.n_groups * blockIdx.x / gridDim.x);
+    const int n_mine = (int)((long long)p.n_groups * (blockIdx.x + 1) / gridDim.x) - g_begin;
+    const int rounds = (n_mine + NW - 1) / NW;
+    const int wpr = rounds > 0 ? (n_mine + rounds - 1) / rounds : 0;      // busy warps per round
+    const uint32_t total_tiles = (uint32_t)rounds * (uint32_t)p.n_tiles;
 
+    // Reference tiles arrive by TMA bulk copies into a ring of p.stages buffers (full[] mbarriers).  There
+    // is no producer warp: every warp counts itself out of a stage when it is done with the tile, and the
+    // last one out re-arms the stage with the tile p.stages ahead - the earliest moment it can be issued.
     const uint32_t plane_bytes = (uint32_t)((size_t)g * WPT * NPL * 4);
-    if (warp == NW) {
-        // ===================== producer: one lane streams the reference tiles =====================
+    auto issue_tile = [&](uint32_t tn, uint32_t s) {          // one thread
+        const int j = (int)(tn % (uint32_t)p.n_tiles);
+        const int n64 = min(2, p.n_tiles64 - 2 * j);
+        const uint32_t ys_bytes = (uint32_t)n64 * g * 64 * 4;
+        ptx::mbar_arrive_expect_tx(&bars->full[s], plane_bytes + ys_bytes);
+        char* dst = reinterpret_cast<char*>(smem + p.stage_off + (size_t)s * p.stage_bytes);
+        const char* src = reinterpret_cast<const char*>(p.planes) + (size_t)j * plane_bytes;
+        for (uint32_t o = 0; o < plane_bytes; o += 16384)
+            ptx::bulk_g2s(dst + o, src + o, min(16384u, plane_bytes - o), &bars->full[s]);
+        dst += plane_bytes;
+        src = reinterpret_cast<const char*>(p.rt) + (size_t)j * 2 * g * 64 * 4;
+        for (uint32_t o = 0; o < ys_bytes; o += 16384)
+            ptx::bulk_g2s(dst + o, src + o, min(16384u, ys_bytes - o), &bars->full[s]);
+    };
+    auto release_tile = [&](uint32_t t, uint32_t s) {         // whole warp, after its last read of the stage
+        __syncwarp();
         if (lane == 0) {
-            uint32_t t = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                for (int j = 0; j < p.n_tiles; ++j, ++t) {
-                    const uint32_t s = t % p.stages, use = t / p.stages;
-                    ptx::mbar_wait(&bars->empty[s], (use & 1) ^ 1);
-                    const int n64 = min(2, p.n_tiles64 - 2 * j);
-                    const uint32_t ys_bytes = (uint32_t)n64 * g * 64 * 4;
-                    ptx::mbar_arrive_expect_tx(&bars->full[s], plane_bytes + ys_bytes);
-                    char* dst = reinterpret_cast<char*>(smem + p.stage_off + (size_t)s * p.stage_bytes);
-                    const char* src = reinterpret_cast<const char*>(p.planes) + (size_t)j * plane_bytes;
-                    for (uint32_t o = 0; o < plane_bytes; o += 16384)
-                        ptx::bulk_g2s(dst + o, src + o, min(16384u, plane_bytes - o), &bars->full[s]);
-                    dst += plane_bytes;
-                    src = reinterpret_cast<const char*>(p.rt) + (size_t)j * 2 * g * 64 * 4;
-                    for (uint32_t o = 0; o < ys_bytes; o += 16384)
-                        ptx::bulk_g2s(dst + o, src + o, min(16384u, ys_bytes - o), &bars->full[s]);
-                }
+            __threadfence_block();
+            if (atomicAdd(&bars->done[s], 1) == NW - 1) {
+                bars->done[s] = 0;
+                __threadfence_block();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (t + p.stages < total_tiles) issue_tile(t + p.stages, s);
             }
         }
-        return;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&bars->full[s], 1); bars->done[s] = 0; }
+        ptx::fence_barrier_init();
+        for (uint32_t tn = 0; tn < (uint32_t)p.stages && tn < total_tiles; ++tn) issue_tile(tn, tn);
     }
+    __syncthreads();
 
     // ===================== consumers: lanes = queries =====================
     float* xs = reinterpret_cast<float*>(smem + p.xs_off) + (size_t)warp * g * 32;
@@ -314,8 +329,18 @@ sliced_kernel(const Params p) {
     };
 
     uint32_t t = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int group = item * NW + warp;
+    for (int round = 0; round < rounds; ++round) {
+        const int gi = round * wpr + warp;
+        if (warp >= wpr || gi >= n_mine) {
+            // no group for this warp in this round: keep the tile ring moving
+            for (int j = 0; j < p.n_tiles; ++j, ++t) {
+                const uint32_t s = t % p.stages, use = t / p.stages;
+                ptx::mbar_wait(&bars->full[s], use & 1);
+                release_tile(t, s);
+            }
+            continue;
+        }
+        const int group = g_begin + gi;
         const long long q_mine = (long long)group * 32 + lane;
         uint32_t ctrl[NB * 4];
 #pragma unroll
@@ -447,11 +472,10 @@ sliced_kernel(const Params p) {
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&bars->empty[s]);
+            release_tile(t, s);
         }
 
-        // ---- item done: exact selection of every query of this warp, emit candidates + threshold
+        // ---- round done: exact selection of every query of this warp, emit candidates + threshold
         for (int src = 0; src < 32; ++src) {
             const int n = s_cnt[src];
             const float old_tau = s_tau[src];
@@ -484,16 +508,16 @@ bool nabo_cbs_supported(int g, int k, int drop_first) {
     return cbs::plan_smem(g).stages >= 2 && ksel + 8 <= cbs::CAP - 64;
 }
 
-static int cbs_grid(int n_items) {
+static int cbs_grid(int n_groups) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return n_items < sms ? n_items : sms;
+    return n_groups < sms ? n_groups : sms;
 }
 
 size_t nabo_cbs_extra_bytes(int n_query, int n_ref, int g) {
     const size_t n_tiles = (n_ref + cbs::RT - 1) / cbs::RT;
-    const size_t n_groups = (size_t)((n_query + cbs::QB - 1) / cbs::QB) * cbs::NW;
+    const size_t n_groups = (size_t)(n_query + 31) / 32;
     const int nj = cbs::nblocks8(g) * 4;
     size_t b = 0;
     b += nabo_align_up(n_tiles * cbs::plane_tile_bytes(g), 256);
@@ -512,10 +536,9 @@ int nabo_cbs_candidates(const double* q, int ldq, const double* r, int ldr, int 
     const cbs::SmemPlan pl = cbs::plan_smem(g);
     const int n_tiles = (n_ref + cbs::RT - 1) / cbs::RT;
     const int n_tiles64 = (n_ref + 63) / 64;
-    const int n_items = (n_query + cbs::QB - 1) / cbs::QB;
-    const size_t n_groups = (size_t)n_items * cbs::NW;
+    const size_t n_groups = (size_t)(n_query + 31) / 32;
     const int nb = cbs::nblocks8(g), nj = nb * 4;
-    const int grid = cbs_grid(n_items);
+    const int grid = cbs_grid((int)n_groups);
 
     NaboArena ar(extra, extra_bytes);
     uint32_t* planes = (uint32_t*)ar.take<char>((size_t)n_tiles * cbs::plane_tile_bytes(g));
@@ -540,7 +563,7 @@ int nabo_cbs_candidates(const double* q, int ldq, const double* r, int ldr, int 
     cbs::Params p;
     p.planes = planes; p.rt = rt; p.qx = qx; p.ctrl = ctrl;
     p.n_query = n_query; p.n_ref = n_ref; p.g = g; p.n_tiles = n_tiles; p.n_tiles64 = n_tiles64;
-    p.n_items = n_items; p.kprime = kprime; p.stages = pl.stages; p.nj = nj;
+    p.n_groups = (int)n_groups; p.kprime = kprime; p.stages = pl.stages; p.nj = nj;
     const double delta = fmax(1e-5, 4e-7 * (2.0 + f) / f);      // same optimistic margin as canberra_candidates.cu
     p.fm = (float)(f * (1.0 + delta));
     p.cand_buf = cbuf; p.cand = cand; p.tau_out = tau;
