@@ -43,6 +43,7 @@ constexpr int LC = 512;                   // work-list entries per warp
 constexpr int CAP = sel::CAP;
 constexpr int MAX_STAGES = 4;
 constexpr int EDGE_SAMPLE = 4096;
+constexpr int TRIG_EXTRA = 24;            // keys above kprime that trigger a compaction
 
 static inline int nblocks8(int g) { return (g + 7) / 8; }
 static inline size_t plane_tile_bytes(int g) { return (size_t)g * WPT * NPL * 4; }
@@ -197,6 +198,7 @@ struct Params {
     const uint32_t* ctrl;       // [n_groups][nj][32]
     int n_query, n_ref, g, n_tiles, n_tiles64, n_groups, kprime, stages, nj;
     float fm;
+    int trig_extra;
     unsigned long long* cand_buf;   // [gridDim][QB][CAP]
     int32_t* cand;              // [n_query][kprime]
     float* tau_out;             // [n_query]
@@ -314,14 +316,17 @@ sliced_kernel(const Params p) {
                 gbuf[(size_t)ql * CAP + pos] = make_key(acc, (uint32_t)(ref0 + rl));
             }
             __syncwarp();
-            // a round adds at most 32 keys to one query: keep every buffer at or below CAP - 32
-            unsigned need = __ballot_sync(0xffffffffu, s_cnt[lane] > CAP - 32);
+            // a round adds at most 32 keys to one query: keep every buffer at or below CAP - 32.  Compacting
+            // earlier than that (kprime + trig_extra keys) keeps tau closer to the true running K'-th best
+            // score: a stale threshold lets proportionally more pairs through to the dense evaluation.
+            const int trig = min(CAP - 32, kprime + p.trig_extra);
+            unsigned need = __ballot_sync(0xffffffffu, s_cnt[lane] > trig);
             while (need) {
                 const int src = __ffs(need) - 1;
                 need &= need - 1;
                 int nc;
                 float nt;
-                compact_select(gbuf + (size_t)src * CAP, s_cnt[src], lane, kprime, CAP - 40, hist, nc, nt);
+                compact_select(gbuf + (size_t)src * CAP, s_cnt[src], lane, kprime, trig - 4 > kprime ? trig - 4 : kprime, hist, nc, nt);
                 if (lane == src) { s_cnt[lane] = nc; s_tau[lane] = nt; }
                 __syncwarp();
             }
@@ -567,6 +572,7 @@ int nabo_cbs_candidates(const double* q, int ldq, const double* r, int ldr, int 
     const double delta = fmax(1e-5, 4e-7 * (2.0 + f) / f);      // same optimistic margin as canberra_candidates.cu
     p.fm = (float)(f * (1.0 + delta));
     p.cand_buf = cbuf; p.cand = cand; p.tau_out = tau;
+    p.trig_extra = cbs::TRIG_EXTRA;
     p.stage_bytes = pl.stage_bytes; p.stage_off = pl.stage_off; p.xs_off = pl.xs_off; p.hist_off = pl.hist_off;
     p.work_off = pl.work_off; p.tau_off = pl.tau_off; p.cnt_off = pl.cnt_off; p.bar_off = pl.bar_off;
 #define NABO_CBS_LAUNCH(NBV)                                                                                       \

@@ -161,3 +161,60 @@ def test_canberra_threshold_adversarial(core, f):
     assert same_bits(fd, ed) and np.array_equal(fi, ei)
     oi, od = O.knn(q[:64], r, k, "mod_canberra", f)
     assert same_bits(fd[:64], od) and np.array_equal(fi[:64], oi)
+
+
+@pytest.mark.parametrize("n,m,g,k,f", [
+    (1, 200, 50, 30, 0.25),            # one query, one warp, two reference tiles
+    (33, 129, 5, 3, 0.25),             # ragged everywhere: 2 query groups, 1 reference beyond a tile, g < 8
+    (1000, 4097, 13, 15, 0.1),         # g = 8 + 5
+    (5000, 30000, 25, 10, 0.25),       # config-1 width
+    (4800, 20000, 50, 30, 0.5),        # 150 query groups: every SM gets one or two
+    (700, 9000, 56, 20, 0.25),         # widest g of the sliced pass
+    (700, 9000, 64, 20, 0.25),         # past it: FP16 two-phase pass
+    (300, 3000, 80, 8, 2.0),           # g > 64: exact engine; f > 1 (intervals straddle zero)
+    (300, 3000, 40, 8, 2.0),
+])
+def test_canberra_sliced_shapes(core, n, m, g, k, f):
+    """Bit-sliced Canberra pass (bin planes + carry-save count + FP32 evaluation): same result as the exact
+    engine over ragged shapes, and the certificate must actually clear the rows (a silently wrong bound
+    would show up as mass fallback, not as a wrong answer)."""
+    from nabo_b200 import synth
+    q = synth.pc_mixture(n, g, seed=7)
+    r = synth.pc_mixture(m, g, seed=8)
+    fi, fd, st = core.knn(q, r, k, "mod_canberra", f, mode="fast", return_stats=True)
+    ei, ed = core.knn(q, r, k, "mod_canberra", f, mode="exact")
+    assert same_bits(fd, ed) and np.array_equal(fi, ei)
+    if g <= 64:                          # wider inputs run on the exact engine by design
+        assert st["rows_exact_fallback"] <= max(2, n // 50)
+
+
+def test_canberra_sliced_degenerate_values(core):
+    """Bin edges and interval ends on awkward data: integer-valued columns (every value sits on a bin edge),
+    constant and all-zero columns (all edges equal, empty intervals), huge / tiny magnitudes, NaN and inf
+    entries, masked references and self-mapping with the first neighbour dropped."""
+    rng = np.random.default_rng(5)
+    n, m, g, k = 900, 6000, 20, 12
+    r = rng.normal(size=(m, g))
+    r[:, 0] = rng.integers(-3, 4, size=m)                 # few distinct values, many exact ties with the edges
+    r[:, 1] = 2.5                                         # constant
+    r[:, 2] = 0.0                                         # zero: |x - y| < f|x| is never true
+    r[:, 3] *= 1e30
+    r[:, 4] *= 1e-30
+    r[:, 5] = np.round(r[:, 5], 1)
+    q = r[rng.choice(m, n, replace=False)] * (1.0 + 0.05 * rng.normal(size=(n, g)))
+    q[:, 0] = rng.integers(-3, 4, size=n)
+    q[5, 7] = np.nan
+    q[6, 8] = np.inf
+    r[17, 9] = np.nan
+    r[18, 9] = -np.inf
+    mask = rng.random(m) < 0.3
+    for kw in (dict(), dict(ref_mask=mask), dict(idx_offset=11)):
+        fi, fd, st = core.knn(q, r, k, "mod_canberra", 0.25, mode="fast", return_stats=True, **kw)
+        ei, ed = core.knn(q, r, k, "mod_canberra", 0.25, mode="exact", **kw)
+        assert same_bits(fd, ed) and np.array_equal(fi, ei)
+    oi, od = O.knn(q[:40], r, k, "mod_canberra", 0.25, mask=mask)
+    fi, fd = core.knn(q[:40], r, k, "mod_canberra", 0.25, ref_mask=mask, mode="fast")
+    assert same_bits(fd, od) and np.array_equal(fi, oi)
+    si, sd = core.knn(r[:2000], r[:2000], k, "mod_canberra", 0.25, drop_first=True, mode="fast")
+    ei, ed = core.knn(r[:2000], r[:2000], k, "mod_canberra", 0.25, drop_first=True, mode="exact")
+    assert same_bits(sd, ed) and np.array_equal(si, ei)
