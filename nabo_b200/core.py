@@ -33,12 +33,13 @@ def _is_host(*xs) -> bool:
 
 
 def _dev(x, dtype: torch.dtype, name: str = "array") -> Optional[torch.Tensor]:
-    """Device tensor of `dtype`, row-major contiguous.  Host arrays travel through pinned memory."""
+    """Device tensor of `dtype`, row-major contiguous.  Host arrays are copied from pageable memory: pinning a
+    buffer for a single use costs more than it saves (map_cells_host is the pre-pinned, pipelined path)."""
     if x is None:
         return None
     if isinstance(x, torch.Tensor):
         if not x.is_cuda:
-            x = x.pin_memory().cuda(non_blocking=True)
+            x = x.cuda()
         if x.dtype != dtype:
             x = x.to(dtype)
         return x.contiguous()
@@ -46,7 +47,7 @@ def _dev(x, dtype: torch.dtype, name: str = "array") -> Optional[torch.Tensor]:
     t = torch.from_numpy(a)
     if t.dtype != dtype:
         t = t.to(dtype)
-    return t.pin_memory().cuda(non_blocking=True)
+    return t.cuda()
 
 
 def _mask_dev(mask) -> Optional[torch.Tensor]:

@@ -215,6 +215,13 @@ class RowGroup(Group):
         self.data = data
         self._index: Optional[Dict[str, int]] = None
         self._sorted: Optional[List[str]] = None
+        self._names_enc: Optional[np.ndarray] = None      # utf-8 byte-string array of row_names (file form)
+
+    def names_encoded(self) -> np.ndarray:
+        if self._names_enc is None:
+            self._names_enc = (np.char.encode(np.asarray(self.row_names, dtype=str), "utf-8")
+                               if len(self.row_names) else np.zeros(0, "S1"))
+        return self._names_enc
 
     def _idx(self) -> Dict[str, int]:
         if self._index is None:
@@ -264,6 +271,17 @@ class RowGroup(Group):
         raise TypeError("RowGroup has fixed membership")
 
 
+# Content of the files this process last read or wrote, keyed by absolute path and valid while the file's
+# (mtime_ns, size) is unchanged: the facade opens the same mapping file once per step (as the reference does
+# with h5py), and re-parsing a container of (cells x k) tables each time would dominate a 20 ms GPU job.
+_CONTENT_CACHE: Dict[str, tuple] = {}
+
+
+def _stat_key(fn: str):
+    st = os.stat(fn)
+    return (st.st_mtime_ns, st.st_size)
+
+
 class File(Group):
     """``File(fn, mode)`` with h5py's mode letters: r, r+, a, w, w-/x."""
 
@@ -293,6 +311,13 @@ class File(Group):
             self._c = MEMORY_FILES[self.filename]._c
             _reroot(self, self)
             return
+        key = os.path.abspath(self.filename)
+        hit = _CONTENT_CACHE.get(key)
+        if hit is not None and hit[0] == _stat_key(self.filename):
+            self._c = hit[1]
+            _reroot(self, self)
+            self._dirty = False
+            return
         with zipfile.ZipFile(self.filename, "r") as z:
             manifest = json.loads(z.read("__manifest__.json").decode("utf-8"))
             for path in manifest["groups"]:
@@ -304,7 +329,8 @@ class File(Group):
             for path, (nkey, dkey) in manifest["rowgroups"].items():
                 names = np.load(io.BytesIO(z.read(nkey)), allow_pickle=False)
                 data = np.load(io.BytesIO(z.read(dkey)), allow_pickle=False)
-                Group.create_row_group(self, path, list(names), data)
+                Group.create_row_group(self, path, list(names), data)._names_enc = names
+        _CONTENT_CACHE[key] = (_stat_key(self.filename), self._c)
         self._dirty = False
 
     def _persist(self):
@@ -332,9 +358,7 @@ class File(Group):
                 for k, v in g._c.items():
                     p = prefix + "/" + k if prefix else k
                     if isinstance(v, RowGroup):
-                        manifest["rowgroups"][p] = [put(np.char.encode(np.asarray(v.row_names, dtype=str), "utf-8")
-                                                        if len(v.row_names) else np.zeros(0, "S1")),
-                                                    put(v.data)]
+                        manifest["rowgroups"][p] = [put(v.names_encoded()), put(v.data)]
                     elif isinstance(v, Group):
                         manifest["groups"].append(p)
                         rec(v, p)
@@ -343,6 +367,7 @@ class File(Group):
             rec(self, "")
             z.writestr("__manifest__.json", json.dumps(manifest))
         os.replace(tmp, self.filename)
+        _CONTENT_CACHE[os.path.abspath(self.filename)] = (_stat_key(self.filename), self._c)
         self._dirty = False
 
     def flush(self):

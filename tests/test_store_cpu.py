@@ -132,3 +132,26 @@ def test_dataset_host_stats_match_reference(tmp_path, golden):
     assert np.array_equal(d2.sf, g["sf_ref"])
     with pytest.raises(ValueError, match="None of the input genes"):
         d.get_scaling_params(["NOPE"])
+
+
+def test_reopen_uses_cached_content_and_notices_foreign_writes(tmp_path):
+    """Reopening a file this process wrote is served from the content cache; a file replaced behind the
+    cache's back (different mtime / size) is parsed again."""
+    import os
+    import shutil
+    from nabo_b200 import store
+    fn, other = str(tmp_path / "a.h5"), str(tmp_path / "b.h5")
+    with store.File(fn, "w") as h:
+        h.create_row_group("data", ["c1", "c2"], np.arange(6.0).reshape(2, 3))
+        h.create_dataset("meta/k", data=np.array([7]))
+    with store.File(fn, "a") as h:                         # cache hit, then a write through it
+        assert h["data"]["c2"][:].tolist() == [3.0, 4.0, 5.0]
+        h.create_dataset("meta/extra", data=np.array([1, 2, 3]))
+    with store.File(fn, "r") as h:
+        assert h["meta/extra"][:].tolist() == [1, 2, 3] and h["meta/k"][0] == 7
+    with store.File(other, "w") as h:
+        h.create_dataset("only", data=np.array([42]))
+    shutil.copyfile(other, fn)                             # foreign writer
+    os.utime(fn, ns=(1, 1))
+    with store.File(fn, "r") as h:
+        assert "only" in h and "data" not in h
