@@ -39,6 +39,13 @@ constexpr int MMA_WARP0 = 13;        // so the single-thread producer / issuers 
 constexpr int TMEM_WARP = 12;
 constexpr int CAP = sel::CAP;        // candidate buffer entries per query
 constexpr int CHUNK = 32;           // columns per tcgen05.ld
+#ifndef NABO_TC_ROTATE
+#define NABO_TC_ROTATE 1
+#endif
+// accumulators in TMEM (128 columns each).  ROTATE: the NQ query tiles share NQ + 1 buffers in a fixed
+// rotation (job n = tile * NQ + q uses buffer n % 4), so the MMAs of a warpgroup's next tile run while it is
+// still reading the current one; otherwise one private buffer per query tile (MMA and epilogue alternate).
+constexpr int NACC = NABO_TC_ROTATE ? 4 : NQ;
 
 __host__ __device__ inline int kp_for(int g) { return (3 * g + 3 + 15) / 16 * 16; }
 __host__ __device__ inline size_t tile_bytes(int kp) { return (size_t)TILE * kp * 2; }
@@ -183,7 +190,7 @@ struct Params {
 struct Barriers {
     uint64_t a_full, a_empty;
     uint64_t b_full[4], b_empty[4];
-    uint64_t acc_full[NQ], acc_empty[NQ];
+    uint64_t acc_full[NACC], acc_empty[NACC];
     uint32_t tmem_base;
 };
 
@@ -234,9 +241,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
 
     if (threadIdx.x == 0) {
         ptx::mbar_init(&bars->a_full, 1);
-        ptx::mbar_init(&bars->a_empty, NQ);
-        for (int s = 0; s < 4; ++s) { ptx::mbar_init(&bars->b_full[s], 1); ptx::mbar_init(&bars->b_empty[s], NQ); }
-        for (int q = 0; q < NQ; ++q) { ptx::mbar_init(&bars->acc_full[q], 1); ptx::mbar_init(&bars->acc_empty[q], 4); }
+        const int n_issuers = NABO_TC_ROTATE ? 1 : NQ;
+        ptx::mbar_init(&bars->a_empty, n_issuers);
+        for (int s = 0; s < 4; ++s) { ptx::mbar_init(&bars->b_full[s], 1); ptx::mbar_init(&bars->b_empty[s], n_issuers); }
+        for (int q = 0; q < NACC; ++q) { ptx::mbar_init(&bars->acc_full[q], 1); ptx::mbar_init(&bars->acc_empty[q], 4); }
         ptx::fence_barrier_init();
     }
     if (warp == TMEM_WARP) ptx::tmem_alloc(&bars->tmem_base, 512);
@@ -269,6 +277,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                 }
             }
         }
+#if NABO_TC_ROTATE
+    } else if (warp == MMA_WARP0) {
+        // ===================== MMA issuer: one warp, jobs in a fixed rotation =====================
+        // Job n = (reference tile, query tile q = n % NQ) accumulates into buffer n % 4.  With one buffer more
+        // than there are warpgroups, the MMAs of job n start as soon as the warpgroup of job n - 4 (the
+        // PREVIOUS query tile, one reference tile back) has read its accumulator - about a third of a period
+        // before warpgroup q finishes its current tile - so they complete while q is still filtering.
+        // The whole warp runs the loop (descriptor arithmetic in the uniform datapath); only the elected
+        // lane issues tcgen05.mma / commit.
+        {
+            const uint32_t idesc = ptx::make_idesc_f16(TILE, TILE);
+            const uint32_t lbo = TILE * 16, sbo = 128;
+            const uint64_t ad0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.a_off), lbo, sbo);
+            const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off), lbo, sbo);
+            uint32_t t = 0, it = 0, n = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+                ptx::mbar_wait(&bars->a_full, it & 1);
+                for (int j = 0; j < p.n_rtiles; ++j, ++t) {
+                    const uint32_t s = t % p.stages, use = t / p.stages;
+                    ptx::mbar_wait(&bars->b_full[s], use & 1);
+                    const uint64_t bd1 = bd0 + (uint64_t)((s * a_tile_bytes) >> 4);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q, ++n) {
+                        const uint32_t buf = n & 3;
+                        ptx::mbar_wait(&bars->acc_empty[buf], ((n >> 2) & 1) ^ 1);
+                        ptx::tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + buf * TILE;
+                        const uint64_t ad1 = ad0 + (uint64_t)((q * a_tile_bytes) >> 4);
+                        if (ptx::elect_one()) {
+                            if (KSTEPS > 0) {
+#pragma unroll
+                                for (int ks = 0; ks < KSTEPS; ++ks)
+                                    ptx::mma_f16_ss(d_tmem, ad1 + ks * ((2 * lbo) >> 4), bd1 + ks * ((2 * lbo) >> 4), idesc,
+                                                    ks > 0 ? 1u : 0u);
+                            } else {
+                                for (int ks = 0; ks < ksteps; ++ks)
+                                    ptx::mma_f16_ss(d_tmem, ad1 + ks * ((2 * lbo) >> 4), bd1 + ks * ((2 * lbo) >> 4), idesc,
+                                                    ks > 0 ? 1u : 0u);
+                            }
+                            ptx::mma_commit(&bars->acc_full[buf]);
+                            if (q == NQ - 1) {
+                                ptx::mma_commit(&bars->b_empty[s]);
+                                if (j == p.n_rtiles - 1) ptx::mma_commit(&bars->a_empty);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+#else
     } else if (warp >= MMA_WARP0 && warp < MMA_WARP0 + NQ) {
         // ===================== MMA issuers: one thread per query tile =====================
         // Each issuer sleeps on its own accumulator's mbarrier (hardware wake-up, no polling loop), so a
@@ -312,13 +371,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                 }
             }
         }
+#endif
     } else if (warp < N_EPI_WARPS) {
         // ===================== epilogue: fused top-K' selection =====================
         const int q = warp >> 2;                           // query tile of this warpgroup
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;
         unsigned long long* mybuf = p.cand_buf + ((size_t)blockIdx.x * NQ * TILE + q * TILE + row) * CAP;
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + q * TILE;
+        const uint32_t tlane0 = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint32_t t = 0;
         uint32_t ks[4], kpl[4];
         uint32_t* hist = reinterpret_cast<uint32_t*>(smem + p.sort_off) + (size_t)warp * 256;
@@ -326,7 +386,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
             float tau = CUDART_INF_F;
             int cnt = 0;
             for (int j = 0; j < p.n_rtiles; ++j, ++t) {
-                ptx::mbar_wait(&bars->acc_full[q], t & 1);
+#if NABO_TC_ROTATE
+                const uint32_t job = t * NQ + q, buf = job & 3, acc_par = (job >> 2) & 1;
+#else
+                const uint32_t buf = q, acc_par = t & 1;
+#endif
+                const uint32_t taddr0 = tlane0 + buf * TILE;
+                ptx::mbar_wait(&bars->acc_full[buf], acc_par);
                 ptx::tc_fence_after();
                 const int col_limit = p.n_ref - j * TILE;        // columns >= col_limit are padding
 #pragma unroll 1
@@ -338,7 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                         // accumulator fully read: hand it back to the MMA warp before filtering
                         ptx::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[q]);
+                        if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[buf]);
                     }
                     filter_chunk(vr, col_limit - c * CHUNK, (uint32_t)(j * TILE + c * CHUNK), tau, mybuf, cnt);
                     // hard limit: the next chunk may append 32 more; soft limit once per tile, after the release
