@@ -142,6 +142,20 @@ int nabo_classify_targets(const int32_t* tgt_knn, const uint8_t* counts, const d
                           double weight_frac, int min_degree, double min_weight,
                           int32_t* out_label, void* stream);
 
+/* Mapping specificity: array form of Graph.get_mapping_specificity (nabo/_graph.py:794-824).
+ * For every target, the unweighted shortest-path lengths in the reference graph (CSR, symmetric:
+ * indptr int64 (n_ref + 1), indices int32) between all pairs of reference cells it has an edge to
+ * (tgt_knn[t][j] with counts[t][j] > 0).  out_sum[t] = sum of d(i, j) over ORDERED pairs (twice the
+ * reference's sum), out_pairs[t] = ordered pairs connected, out_nmapped[t] = mapped cells; the mean is
+ * (out_sum / 2) / (nmapped (nmapped - 1) / 2); out_pairs < nmapped (nmapped - 1) means "no path"
+ * (the reference raises NetworkXNoPath), nmapped < 2 means "no pairs" (the reference's NaN).
+ * One bit-parallel multi-source BFS per target instead of one BFS per pair; k <= 64. */
+size_t nabo_specificity_workspace_bytes(int n_ref, int n_query);
+int nabo_mapping_specificity(const long long* indptr, const int32_t* indices, int n_ref,
+                             const int32_t* tgt_knn, const uint8_t* counts, int n_query, int k,
+                             long long* out_sum, int32_t* out_pairs, int32_t* out_nmapped,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- (6) scaling + PCA projection: replaces get_scaled_values + transform_pca ---
  * nabo/_dataset.py:905-913 and :1028 (sklearn IncrementalPCA.transform):
  *   a = counts as float32; z = ((a * sf_i) [float32] - mu) / sigma   [float64]

@@ -45,6 +45,8 @@ SIGNATURES: Dict[str, tuple] = {
     "nabo_scores_workspace_bytes": (_z, [_i, _i, _i]),
     "nabo_mapping_scores": (_i, [_p, _p, _p, _i, _i, _i, _p, _i, _d, _i, _d, _d, _p, _p, _z, _p]),
     "nabo_classify_targets": (_i, [_p, _p, _p, _i, _i, _p, _i, _d, _i, _d, _p, _p]),
+    "nabo_specificity_workspace_bytes": (_z, [_i, _i]),
+    "nabo_mapping_specificity": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _z, _p]),
     "nabo_scale_dense": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p, _i, _p]),
     "nabo_project_dense": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _i, _p]),
     "nabo_project_csr_workspace_bytes": (_z, [_i, _i]),

@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import METRICS, MODE_EXACT, MODE_FAST, check, lib, require_device
 
 __all__ = ["euclidean_dist", "mod_canberra_dist", "cosine_dist", "knn", "knn_candidates", "rerank_exact", "merge_topk",
-           "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets",
+           "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets", "mapping_specificity",
            "project", "project_csr", "scale_counts", "map_cells", "map_cells_host", "resolve_metric"]
 
 
@@ -320,6 +320,35 @@ def classify_targets(tgt_knn, counts, ref_labels, n_labels: int, k: Optional[int
                                       float(weight_frac), int(min_degree), float(min_weight), _ptr(out),
                                       C.c_void_p(_stream())), "classify_targets")
     return _out(out, host)
+
+
+def mapping_specificity(indptr, indices, tgt_knn, counts):
+    """Array form of ``Graph.get_mapping_specificity`` (nabo/_graph.py:794-824): per target, the mean
+    unweighted shortest-path length in the reference graph (symmetric CSR ``indptr`` int64, ``indices``
+    int32) between all pairs of reference cells the target has an edge to (``counts > 0``).
+    Returns (mean float64 (N,) with NaN where fewer than two cells are mapped, connected bool (N,) -
+    False where some pair has no path, which is where the reference raises NetworkXNoPath)."""
+    require_device()
+    host = _is_host(indptr, indices, tgt_knn, counts)
+    ip, ix = _dev(indptr, torch.int64), _dev(indices, torch.int32)
+    td, cd = _dev(tgt_knn, torch.int32), _dev(counts, torch.uint8)
+    n, kk = td.shape
+    m = ip.numel() - 1
+    if cd.shape != td.shape:
+        raise ValueError("ERROR: tgt_knn and counts must have the same shape")
+    osum = torch.empty(n, dtype=torch.int64, device=td.device)
+    opairs = torch.empty(n, dtype=torch.int32, device=td.device)
+    onm = torch.empty(n, dtype=torch.int32, device=td.device)
+    wb = lib().nabo_specificity_workspace_bytes(m, n)
+    ws = torch.empty(max(wb, 1), dtype=torch.uint8, device=td.device)
+    check(lib().nabo_mapping_specificity(_ptr(ip), _ptr(ix), m, _ptr(td), _ptr(cd), n, kk, _ptr(osum), _ptr(opairs),
+                                         _ptr(onm), _ptr(ws), ws.numel(), C.c_void_p(_stream())), "mapping_specificity")
+    nm = onm.to(torch.int64)
+    want = nm * (nm - 1)
+    mean = torch.where(nm >= 2, (osum // 2).to(torch.float64) / (want // 2).clamp(min=1).to(torch.float64),
+                       torch.full((n,), float("nan"), dtype=torch.float64, device=td.device))
+    connected = opairs.to(torch.int64) >= want
+    return _out(mean, host), _out(connected, host)
 
 
 # ----------------------------------------------------------------------------- (6) projection

@@ -1,13 +1,14 @@
 """``Graph``: the part of ``nabo.Graph`` (nabo/_graph.py) that sits on the hot path.
 
 Kept verbatim: ``Graph()`` (an ``nx.Graph``), ``load_from_h5(fn, name, kind)``,
-``get_mapping_score(target, ...)`` with every keyword, ``classify_target`` and the attributes
+``get_mapping_score(target, ...)`` with every keyword, ``classify_target``,
+``get_mapping_specificity`` / ``get_ref_specificity`` and the attributes
 ``refName, refNodes, refG, targetNames, targetNodes``.  The per-reference score and the
 per-target cluster vote run on the GPU from the columnar graph arrays (``knn``, ``snn``)
 that ``Mapping.calc_snn`` stores; the networkx structure is still populated so that
 downstream networkx code keeps working (``materialize=False`` skips that for large graphs).
 The rest of ``nabo.Graph`` (layouts, clustering, GML, DE helpers; nabo/_graph.py:118-554,
-794-1055) is downstream analytics on the result and is out of scope.
+858-1055) is downstream analytics on the result and is out of scope.
 """
 from __future__ import annotations
 
@@ -17,6 +18,7 @@ from typing import Dict, List, Optional
 
 import networkx as nx
 import numpy as np
+import pandas as pd
 
 from . import core
 from .store import Group, open_file
@@ -148,6 +150,7 @@ class Graph(nx.Graph):
             w = list(w)
             if "fix_edges" in g:
                 fw = float(g["fix_weight"][0])
+                self._samples[name].fix_edges = np.asarray(g["fix_edges"][:], dtype=np.int64)
                 for x, y in np.asarray(g["fix_edges"][:]):
                     a.append(nodes[int(x)])
                     b.append(nodes[int(y)])
@@ -291,6 +294,77 @@ class Graph(nx.Graph):
                     counts[i] = 0
             return counts
         return dict(zip(s.nodes, classified))
+
+
+    # ------------------------------------------------------------------ mapping specificity
+    def _ref_csr(self):
+        """Symmetric CSR adjacency of the reference graph over reference-cell indices."""
+        import scipy.sparse as sp
+        m = len(self._refIndex)
+        s = self._samples.get(self.refName)
+        if s is not None and s.snn is not None:
+            rows, cols = np.nonzero(s.snn > 0)
+            a, b = rows.astype(np.int64), s.knn[rows, cols].astype(np.int64)
+            fx = getattr(s, "fix_edges", None)
+            if fx is not None and len(fx):
+                a, b = np.concatenate([a, fx[:, 0]]), np.concatenate([b, fx[:, 1]])
+        else:                                              # per-node layout: walk the networkx graph
+            ea = [(self._refIndex[x], self._refIndex[y]) for x, y in self.refG.edges()]
+            a = np.array([e[0] for e in ea], dtype=np.int64)
+            b = np.array([e[1] for e in ea], dtype=np.int64)
+        keep = a != b
+        a, b = a[keep], b[keep]
+        adj = sp.coo_matrix((np.ones(2 * len(a), np.int8), (np.concatenate([a, b]), np.concatenate([b, a]))),
+                            shape=(m, m)).tocsr()
+        adj.sum_duplicates()
+        return adj.indptr.astype(np.int64), adj.indices.astype(np.int32)
+
+    def get_mapping_specificity(self, target_name: str, fill_na: bool = True) -> Dict[str, float]:
+        """nabo/_graph.py:794-824 on the GPU: mean unweighted shortest-path length in the reference graph
+        between all pairs of reference nodes a target node maps to (one bit-parallel multi-source BFS per
+        target instead of one networkx BFS per pair).  NaN for targets with fewer than two mapped nodes
+        (replaced by the largest value when ``fill_na``); ``networkx.NetworkXNoPath`` when two mapped nodes
+        are not connected, as upstream."""
+        s = self._samples[target_name]
+        if s.snn is not None:
+            cnt = (s.snn > 0).astype(np.uint8)
+        else:
+            cnt = (s.weights > 0).astype(np.uint8)
+        indptr, indices = self._ref_csr()
+        mean, connected = core.mapping_specificity(indptr, indices, s.knn, cnt)
+        if not bool(np.all(connected)):
+            bad = s.nodes[int(np.nonzero(~connected)[0][0])]
+            raise nx.NetworkXNoPath("No path between two of the reference nodes that %s maps to." % bad)
+        path_lengths = {n: float(v) for n, v in zip(s.nodes, mean)}
+        if fill_na:
+            max_val = max(path_lengths.values())            # NaN-propagating exactly like the builtin upstream
+            return pd.Series(path_lengths).fillna(max_val).to_dict()
+        return path_lengths
+
+    def get_ref_specificity(self, target: str, target_values: Dict[str, float],
+                            incl_unmapped: bool = False) -> Dict[str, float]:
+        """nabo/_graph.py:826-857: mean specificity of the target nodes mapped to each reference node
+        (adjacency order = target order, as upstream)."""
+        s = self._samples[target]
+        mask = (s.snn > 0) if s.snn is not None else (s.weights > 0)
+        rows, cols = np.nonzero(mask)
+        refs = s.knn[rows, cols]
+        order = np.argsort(refs, kind="stable")             # per reference node: its targets in target order
+        refs, rows = refs[order], rows[order]
+        vals = np.array([target_values[n] for n in s.nodes], dtype=np.float64)[rows]
+        bounds = np.flatnonzero(np.r_[True, refs[1:] != refs[:-1], True])
+        names = {i: n for n, i in self._refIndex.items()}
+        out: Dict[str, float] = {}
+        have = set()
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            r = int(refs[lo])
+            have.add(r)
+            out[names[r]] = np.mean(vals[lo:hi]) if hi - lo > 1 else vals[lo]
+        if incl_unmapped:
+            for n, i in self._refIndex.items():
+                if i not in have:
+                    out[n] = 0
+        return {n: out[n] for n in self.refNodes if n in out}
 
 
 def _scores_from_weights(knn, weights, n_ref, mask, min_weight, weighted, mult):

@@ -325,3 +325,40 @@ def merge_topk(idx_shards, dist_shards, k: int):
     key = np.where(np.isnan(dst), np.inf, dst)
     order = np.lexsort((idx, key), axis=1)[:, :k]
     return np.take_along_axis(idx, order, 1), np.take_along_axis(dst, order, 1)
+
+
+def mapping_specificity(ref_edges_a, ref_edges_b, n_ref, tgt_knn, tgt_counts):
+    """Graph.get_mapping_specificity (nabo/_graph.py:794-824), array form: for every target the mean
+    unweighted shortest-path length (hops) in the undirected reference graph given by the edge list
+    (a[i], b[i]) between all pairs i < j of reference cells it has an edge to (counts > 0).
+    NaN with fewer than two mapped cells (np.mean of an empty list upstream); raises ValueError when
+    a pair is not connected (networkx.NetworkXNoPath upstream).  Plain BFS per source, small cases only."""
+    adj = [[] for _ in range(n_ref)]
+    for x, y in zip(ref_edges_a, ref_edges_b):
+        x, y = int(x), int(y)
+        if x != y:
+            adj[x].append(y)
+            adj[y].append(x)
+    out = np.full(len(tgt_knn), np.nan)
+    for t in range(len(tgt_knn)):
+        mapped = [int(r) for r, c in zip(tgt_knn[t], tgt_counts[t]) if c > 0 and r >= 0]
+        if len(mapped) < 2:
+            continue
+        spls = []
+        for i, src in enumerate(mapped):
+            dist = {src: 0}
+            frontier = [src]
+            while frontier:
+                nxt = []
+                for u in frontier:
+                    for v in adj[u]:
+                        if v not in dist:
+                            dist[v] = dist[u] + 1
+                            nxt.append(v)
+                frontier = nxt
+            for dst in mapped[i + 1:]:
+                if dst not in dist:
+                    raise ValueError("no path between reference cells %d and %d" % (src, dst))
+                spls.append(dist[dst])
+        out[t] = float(np.mean(spls))
+    return out

@@ -18,6 +18,7 @@ of the plotting modules, never called here).
     python tests/golden/make_golden.py          # rewrites tests/golden/*.npz
 """
 import os
+import warnings
 import random
 import sys
 import tempfile
@@ -171,6 +172,17 @@ def run_mapping(nabo, tmp, ref, tgt, ref_names, tgt_names, use_comps, k, f, chun
                      ("score_minscore", dict(min_score=2.0))):
         sc = g.get_mapping_score("TGT", **kw)
         res[name] = np.array([sc[n + "_REF"] for n in sref], dtype=np.float64)
+    # mapping specificity (nabo/_graph.py:794-857): raw (NaN kept), NaN-filled, and folded back on the reference
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sp_raw = g.get_mapping_specificity("TGT", fill_na=False)
+        sp_fill = g.get_mapping_specificity("TGT", fill_na=True)
+    res["specificity_raw"] = np.array([sp_raw[n + "_TGT"] for n in stgt], dtype=np.float64)
+    res["specificity_filled"] = np.array([sp_fill[n + "_TGT"] for n in stgt], dtype=np.float64)
+    rs = g.get_ref_specificity("TGT", sp_fill)
+    res["ref_specificity"] = np.array([rs.get(n + "_REF", np.nan) for n in sref], dtype=np.float64)
+    rs0 = g.get_ref_specificity("TGT", sp_fill, incl_unmapped=True)
+    res["ref_specificity_unmapped0"] = np.array([rs0[n + "_REF"] for n in sref], dtype=np.float64)
     return res
 
 

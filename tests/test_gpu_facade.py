@@ -118,6 +118,22 @@ def test_mapping_graph_end_to_end(tmp_path, golden, name, per_cell):
     g2.load_from_h5(map_fn, "REF", "reference")
     g2.load_from_h5(map_fn, "TGT", "target")
     assert g2.get_mapping_score("TGT") == gph.get_mapping_score("TGT")
+    # mapping specificity: the reference's own values (networkx BFS per pair) from one multi-source BFS per target
+    if same_lists:
+        sp = gph.get_mapping_specificity("TGT", fill_na=False)
+        got_sp = np.array([sp[c + "_TGT"] for c in tn])
+        assert np.array_equal(np.isnan(got_sp), np.isnan(g["specificity_raw"]))
+        ok = ~np.isnan(got_sp)
+        assert np.array_equal(got_sp[ok], g["specificity_raw"][ok])
+        spf = gph.get_mapping_specificity("TGT")
+        assert np.array_equal(np.array([spf[c + "_TGT"] for c in tn]), g["specificity_filled"], equal_nan=True)
+        rs = gph.get_ref_specificity("TGT", spf)
+        exp_rs = g["ref_specificity"]
+        assert sorted(rs) == sorted(rn[i] + "_REF" for i in np.nonzero(~np.isnan(exp_rs))[0])
+        assert all(rs[rn[i] + "_REF"] == exp_rs[i] for i in np.nonzero(~np.isnan(exp_rs))[0])
+        rs0 = gph.get_ref_specificity("TGT", spf, incl_unmapped=True)
+        assert np.array_equal(np.array([rs0[c + "_REF"] for c in rn]), g["ref_specificity_unmapped0"])
+        assert list(rs0) == gph.refNodes
     # classification against the oracle
     labels = {c + "_REF": str(i % 4) for i, c in enumerate(rn)}
     gph.import_clusters(labels)

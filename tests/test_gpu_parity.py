@@ -301,3 +301,43 @@ def test_map_cells_host_pipeline_equals_device_path(core):
     assert torch.equal(h["weights"], a["weights"].cpu()) and torch.equal(h["scores"], a["scores"].cpu())
     h2 = core.map_cells_host(torch.from_numpy(tgt).pin_memory(), ref, rk, k, metric="euclidean", chunks=1)
     assert torch.equal(h2["scores"], a["scores"].cpu())
+
+
+@pytest.mark.parametrize("m,n,k,deg,comps", [(500, 300, 8, 3, 1), (4000, 600, 30, 2, 1), (2000, 400, 12, 2, 3),
+                                             (300, 100, 64, 4, 1)])
+def test_mapping_specificity_matches_oracle(core, m, n, k, deg, comps):
+    """Bit-parallel multi-source BFS == one BFS per source (oracle) on sparse random graphs: long paths,
+    targets with 0 / 1 / many mapped cells, padding (-1) entries, and - with several components - pairs
+    without a path, which must be flagged (the reference raises there)."""
+    rng = np.random.default_rng(m + k)
+    comp = rng.integers(0, comps, size=m)
+    a, b = [], []
+    for c in range(comps):
+        nodes = np.nonzero(comp == c)[0]
+        ring = np.roll(nodes, 1)                                   # connected inside a component
+        a += list(nodes); b += list(ring)
+        for _ in range(deg - 1):
+            a += list(nodes); b += list(rng.permutation(nodes))
+    a, b = np.array(a), np.array(b)
+    import scipy.sparse as sp
+    keep = a != b
+    adj = sp.coo_matrix((np.ones(2 * keep.sum(), np.int8), (np.r_[a[keep], b[keep]], np.r_[b[keep], a[keep]])),
+                        shape=(m, m)).tocsr()
+    adj.sum_duplicates()
+    knn = np.stack([rng.choice(m, k, replace=False) for _ in range(n)]).astype(np.int32)
+    cnt = (rng.random((n, k)) < 0.6).astype(np.uint8)
+    cnt[0] = 0                                                      # nothing mapped
+    cnt[1] = 0; cnt[1, 3] = 1                                       # one cell mapped
+    knn[2, ::2] = -1                                                # padding entries are not edges
+    if comps > 1:
+        same = np.array([len(set(comp[r] for r, c in zip(knn[t], cnt[t]) if c and r >= 0)) <= 1 for t in range(n)])
+    else:
+        same = np.ones(n, dtype=bool)
+    mean, connected = core.mapping_specificity(adj.indptr.astype(np.int64), adj.indices.astype(np.int32), knn, cnt)
+    assert np.array_equal(connected, same)
+    sel = np.nonzero(same)[0]
+    exp = O.mapping_specificity(a, b, m, knn[sel], cnt[sel])
+    assert np.array_equal(np.isnan(mean[sel]), np.isnan(exp))
+    ok = ~np.isnan(exp)
+    assert np.array_equal(mean[sel][ok], exp[ok])
+    assert np.isnan(mean[0]) and np.isnan(mean[1])

@@ -188,3 +188,30 @@ def test_c_port_matches_golden_and_numpy(golden):
     lut = O.snn_weight_lut(k)
     np.testing.assert_allclose(c_port.scores(i2, cnt, lut, ref.shape[0]), O.mapping_scores(i2, lut[cnt], ref.shape[0]),
                                rtol=1e-13)
+
+
+def _mapped_arrays(g):
+    """(N, kmax) reference indices per target (-1 padded) + 0/1 counts from the golden target edge list."""
+    n = len(g["tgt"])
+    t, r = g["tgt_edge_t"].astype(int), g["tgt_edge_r"].astype(int)
+    kmax = max(1, int(np.bincount(t, minlength=n).max()))
+    knn = np.full((n, kmax), -1, dtype=np.int32)
+    cnt = np.zeros((n, kmax), dtype=np.uint8)
+    fill = np.zeros(n, dtype=int)
+    for a, b in zip(t, r):
+        knn[a, fill[a]] = b
+        cnt[a, fill[a]] = 1
+        fill[a] += 1
+    return knn, cnt
+
+
+@pytest.mark.parametrize("name", ["mapping_small", "mapping_ignore"])
+def test_mapping_specificity_matches_reference(golden, name):
+    """Graph.get_mapping_specificity of the unmodified reference (networkx BFS per pair) == BFS restatement."""
+    g = golden(name)
+    knn, cnt = _mapped_arrays(g)
+    got = O.mapping_specificity(g["ref_edge_a"], g["ref_edge_b"], len(g["ref"]), knn, cnt)
+    exp = g["specificity_raw"]
+    assert np.array_equal(np.isnan(got), np.isnan(exp))
+    assert np.array_equal(got[~np.isnan(exp)], exp[~np.isnan(exp)])
+    assert np.isnan(exp).sum() == (cnt.sum(1) < 2).sum()

@@ -33,4 +33,6 @@ gph.load_from_h5(map_fn, "TGT", "target")
 t = lap("Graph.load_from_h5 target", t)
 sc = gph.get_mapping_score("TGT")
 t = lap("get_mapping_score", t)
+sp = gph.get_mapping_specificity("TGT")
+t = lap("get_mapping_specificity (GPU multi-source BFS)", t)
 print("total %.3f s; %d scores, max %.3f" % (t - t_all, len(sc), max(sc.values())))
