@@ -48,7 +48,8 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
         char* extra = ar.take<char>(cb_extra_bytes(n_query, n_ref, g));
         if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
         NABO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
-        int rc = nabo_cbs_supported(g, k, drop_first)
+        const bool sliced = nabo_cbs_supported(g, k, drop_first);
+        int rc = sliced
                      ? nabo_cbs_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, rt, extra,
                                            cb_extra_bytes(n_query, n_ref, g), cand, tau, st)
                      : nabo_cb_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, qt, rt, extra, cand,
@@ -69,7 +70,8 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
             int nfail = 0;
             NABO_CUDA(cudaMemcpyAsync(&nfail, fail_count, sizeof(int), cudaMemcpyDeviceToHost, st));
             NABO_CUDA(cudaStreamSynchronize(st));
-            stats_host[0] = n_query; stats_host[1] = nfail; stats_host[2] = kprime; stats_host[3] = 11;
+            stats_host[0] = n_query; stats_host[1] = nfail; stats_host[2] = kprime;
+            stats_host[3] = sliced ? 10 : 11;      // preparation + candidate pass + re-rank + 3 fallback kernels
             stats_host[4] = tm.ns(0); stats_host[5] = tm.ns(1); stats_host[6] = tm.ns(2);
         }
         return 0;
