@@ -156,6 +156,18 @@ int nabo_mapping_specificity(const long long* indptr, const int32_t* indices, in
                              long long* out_sum, int32_t* out_pairs, int32_t* out_nmapped,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* Per-row float32 statistics of a sparse count matrix in NumPy's pairwise summation order: the device
+ * form of Dataset.set_sf (nabo/_dataset.py:573-583: temp[keepGenesIdx].sum() per cell) and
+ * Dataset.set_gene_stats (:609-622: temp.mean(), temp[temp > 0].mean(), temp.var(), (temp > 0).sum() per
+ * gene, temp = densified counts of the kept cells times their size factors).  CSR rows (indptr int64,
+ * idx int32 ascending within a row, val float32); pos_of_col[n_cols] = position of a column in the dense
+ * vector of length n_dense or -1; scale (n_dense) or NULL.  want_moments = 0 fills out_sum only.
+ * Results are bit-identical to NumPy's float32 reductions of the dense vector. */
+int nabo_sparse_row_stats(const long long* indptr, const int32_t* idx, const float* val, int n_rows,
+                          int n_cols, const int32_t* pos_of_col, const float* scale, long long n_dense,
+                          int want_moments, float* out_sum, float* out_mean, float* out_nzmean,
+                          float* out_var, int32_t* out_npos, void* stream);
+
 /* ---- (6) scaling + PCA projection: replaces get_scaled_values + transform_pca ---
  * nabo/_dataset.py:905-913 and :1028 (sklearn IncrementalPCA.transform):
  *   a = counts as float32; z = ((a * sf_i) [float32] - mu) / sigma   [float64]

@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import METRICS, MODE_EXACT, MODE_FAST, check, lib, require_device
 
 __all__ = ["euclidean_dist", "mod_canberra_dist", "cosine_dist", "knn", "knn_candidates", "rerank_exact", "merge_topk",
-           "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets", "mapping_specificity",
+           "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets", "mapping_specificity", "sparse_row_stats",
            "project", "project_csr", "scale_counts", "map_cells", "map_cells_host", "resolve_metric"]
 
 
@@ -349,6 +349,33 @@ def mapping_specificity(indptr, indices, tgt_knn, counts):
                        torch.full((n,), float("nan"), dtype=torch.float64, device=td.device))
     connected = opairs.to(torch.int64) >= want
     return _out(mean, host), _out(connected, host)
+
+
+def sparse_row_stats(indptr, idx, val, pos_of_col, n_dense: int, scale=None, moments: bool = True):
+    """Float32 row statistics of a CSR count matrix in NumPy's pairwise order (``Dataset.set_sf`` /
+    ``set_gene_stats``, nabo/_dataset.py:573-583, 609-622): for every row, the dense vector of length
+    ``n_dense`` (column c sits at ``pos_of_col[c]``, -1 = dropped; values times ``scale``) is reduced exactly
+    like ``temp.sum()``, ``temp.mean()``, ``temp[temp > 0].mean()``, ``temp.var()``, ``(temp > 0).sum()``.
+    Returns dict(sum[, mean, nzmean, var, npos]) - NumPy if the inputs were."""
+    require_device()
+    host = _is_host(indptr, idx, val)
+    ip, ix, vl = _dev(indptr, torch.int64), _dev(idx, torch.int32), _dev(val, torch.float32)
+    pc = _dev(pos_of_col, torch.int32)
+    sc = _dev(scale, torch.float32) if scale is not None else None
+    n_rows = ip.numel() - 1
+    if sc is not None and sc.numel() != n_dense:
+        raise ValueError("ERROR: scale must have one entry per dense position")
+    dev = ip.device
+    out = {"sum": torch.empty(n_rows, dtype=torch.float32, device=dev)}
+    if moments:
+        out.update(mean=torch.empty(n_rows, dtype=torch.float32, device=dev),
+                   nzmean=torch.empty(n_rows, dtype=torch.float32, device=dev),
+                   var=torch.empty(n_rows, dtype=torch.float32, device=dev),
+                   npos=torch.empty(n_rows, dtype=torch.int32, device=dev))
+    check(lib().nabo_sparse_row_stats(_ptr(ip), _ptr(ix), _ptr(vl), n_rows, pc.numel(), _ptr(pc), _ptr(sc), int(n_dense),
+                                      1 if moments else 0, _ptr(out["sum"]), _ptr(out.get("mean")), _ptr(out.get("nzmean")),
+                                      _ptr(out.get("var")), _ptr(out.get("npos")), C.c_void_p(_stream())), "sparse_row_stats")
+    return {k_: _out(v, host) for k_, v in out.items()}
 
 
 # ----------------------------------------------------------------------------- (6) projection

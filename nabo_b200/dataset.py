@@ -144,18 +144,19 @@ class Dataset:
             for i in sf:
                 self.sf[self.cellIdx[i]] = size_scale / sf[i]
         else:
-            self.sf = np.ones(self.rawNCells, dtype=np.float32)
             ip, ix, vl = self._counts_csr()
-            keep = np.zeros(self.rawNGenes, dtype=bool)
-            keep[self.keepGenesIdx] = True
-            for i in range(self.rawNCells):
-                # float32 accumulation over the dense gene vector, as temp[...].sum() upstream
-                temp = np.zeros(self.rawNGenes, dtype=np.float32)
-                temp[ix[ip[i]:ip[i + 1]]] = vl[ip[i]:ip[i + 1]]
-                tot = temp.sum() if all_genes else temp[self.keepGenesIdx].sum()
-                if tot == 0:
-                    tot = 1
-                self.sf[i] = size_scale / tot
+            # float32 pairwise sum of the dense (kept-)gene vector of every cell, as `temp[...].sum()` upstream:
+            # one GPU thread per cell walks NumPy's summation tree (nabo_sparse_row_stats)
+            if all_genes:
+                pos = np.arange(self.rawNGenes, dtype=np.int32)
+                n_dense = self.rawNGenes
+            else:
+                pos = np.full(self.rawNGenes, -1, dtype=np.int32)
+                pos[self.keepGenesIdx] = np.arange(len(self.keepGenesIdx), dtype=np.int32)
+                n_dense = len(self.keepGenesIdx)
+            tot = core.sparse_row_stats(ip, ix, vl, pos, n_dense, moments=False)["sum"]     # float32, as temp.sum()
+            tot[tot == 0] = 1
+            self.sf = (size_scale / tot).astype(np.float32)         # float32 division, like `size_scale / temp_sf`
         h5 = open_file(self.h5Fn, mode="a")
         grp = h5["processed_data"]
         if "sf" in grp:
@@ -166,27 +167,24 @@ class Dataset:
 
     def set_gene_stats(self) -> None:
         """nabo/_dataset.py:594-637: per kept gene, float32 mean / non-zero mean / population variance of
-        the size-factor-normalised values over kept cells (each gene reduced on a contiguous float32 vector,
-        so the statistics - and hence mu, sigma - are bit-identical to upstream)."""
+        the size-factor-normalised values over kept cells, reduced on the GPU in NumPy's float32 pairwise
+        order (nabo_sparse_row_stats), so the statistics - and hence mu, sigma - are bit-identical to upstream."""
         import scipy.sparse as sp
         ip, ix, vl = self._counts_csr()
         csc = sp.csr_matrix((vl, ix, ip), shape=(self.rawNCells, self.rawNGenes)).tocsc()
+        csc.sort_indices()
+        pos = np.full(self.rawNCells, -1, dtype=np.int32)
+        pos[self.keepCellsIdx] = np.arange(len(self.keepCellsIdx), dtype=np.int32)
+        st = core.sparse_row_stats(csc.indptr.astype(np.int64), csc.indices.astype(np.int32),
+                                   csc.data.astype(np.float32), pos, len(self.keepCellsIdx),
+                                   scale=self.sf[self.keepCellsIdx])
         keep_genes = set(int(x) for x in self.keepGenesIdx)
-        sfk = self.sf[self.keepCellsIdx]
         stats = {}
         for i in range(self.rawNGenes):
             gene = self.genes[i]
-            if i in keep_genes:
-                temp = np.zeros(self.rawNCells, dtype=np.float32)
-                lo, hi = csc.indptr[i], csc.indptr[i + 1]
-                temp[csc.indices[lo:hi]] = csc.data[lo:hi]
-                temp = temp[self.keepCellsIdx] * sfk
-                idx = temp > 0
-                if idx.sum() == 0:
-                    stats[gene] = {"valid_gene": False}
-                else:
-                    stats[gene] = {"m": temp.mean(), "nzm": temp[idx].mean(), "variance": temp.var(),
-                                   "valid_gene": True, "ncells": (temp > 0).sum()}
+            if i in keep_genes and st["npos"][i] > 0:
+                stats[gene] = {"m": st["mean"][i], "nzm": st["nzmean"][i], "variance": st["var"][i],
+                               "valid_gene": True, "ncells": st["npos"][i]}
             else:
                 stats[gene] = {"valid_gene": False}
         df = pd.DataFrame(stats).T

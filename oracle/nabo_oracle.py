@@ -362,3 +362,33 @@ def mapping_specificity(ref_edges_a, ref_edges_b, n_ref, tgt_knn, tgt_counts):
                 spls.append(dist[dst])
         out[t] = float(np.mean(spls))
     return out
+
+
+def size_factor_sums(indptr, idx, val, n_cols, keep_cols):
+    """Dataset.set_sf (nabo/_dataset.py:573-583): float32 `temp[keepGenesIdx].sum()` of every cell's densified
+    count vector (NumPy's own float32 pairwise reduction).  CSR over all cells / all genes."""
+    out = np.zeros(len(indptr) - 1, dtype=np.float32)
+    for i in range(len(out)):
+        temp = np.zeros(n_cols, dtype=np.float32)
+        temp[idx[indptr[i]:indptr[i + 1]]] = val[indptr[i]:indptr[i + 1]]
+        out[i] = temp[keep_cols].sum()
+    return out
+
+
+def gene_stats(indptr, idx, val, n_cells, keep_cells, sf):
+    """Dataset.set_gene_stats (nabo/_dataset.py:609-622) for the genes of a gene-major CSR (= CSC of the count
+    matrix): temp = densified counts of the kept cells times their size factors (float32), then
+    m = temp.mean(), nzm = temp[temp > 0].mean(), variance = temp.var(), ncells = (temp > 0).sum()."""
+    n = len(indptr) - 1
+    m, nzm, var = (np.zeros(n, np.float32) for _ in range(3))
+    nc = np.zeros(n, np.int64)
+    sfk = np.asarray(sf, np.float32)[keep_cells]
+    for i in range(n):
+        temp = np.zeros(n_cells, dtype=np.float32)
+        temp[idx[indptr[i]:indptr[i + 1]]] = val[indptr[i]:indptr[i + 1]]
+        temp = temp[keep_cells] * sfk
+        pos = temp > 0
+        nc[i] = pos.sum()
+        if nc[i]:
+            m[i], nzm[i], var[i] = temp.mean(), temp[pos].mean(), temp.var()
+    return m, nzm, var, nc

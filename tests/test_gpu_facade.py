@@ -183,3 +183,64 @@ def test_dataset_projection_pipeline(tmp_path, golden):
         sp2 = sp.rename(index={hvg[0]: "NOT_A_GENE"})
         dt.transform_pca(str(tmp_path / "x.h5"), "data", Model, sp2)
     dt.transform_pca(str(tmp_path / "y.h5"), "data", Model, sp2, fill_missing=True)   # missing gene -> value 0
+
+
+def test_dataset_stats_on_device_match_reference(tmp_path, golden):
+    """set_sf / set_gene_stats / get_scaling_params run on the GPU (NumPy's pairwise order): bit-identical
+    mu, sigma, sf to the unmodified reference."""
+    from nabo_b200.dataset import Dataset, write_dataset
+    g = golden("dataset_small")
+    counts = g["counts_ref"].astype(np.int64)
+    genes = ["G%04d" % i for i in range(counts.shape[1])]
+    cells = ["R%04d" % i for i in range(counts.shape[0])]
+    fn = str(tmp_path / "ref.h5")
+    write_dataset(fn, counts, cells, genes)
+    d = Dataset(fn, force_recalc=True)
+    assert d.cells == cells and d.genes == genes
+    d.set_sf()
+    assert d.sf.dtype == np.float32 and np.array_equal(d.sf, g["sf_ref"])
+    d.set_gene_stats()
+    hvg = [genes[i] for i in g["gene_idx"]]
+    sp = d.get_scaling_params(hvg)
+    assert np.array_equal(sp["mu"].values, g["mu"]) and np.array_equal(sp["sigma"].values, g["sigma"])
+    assert np.array_equal(d.geneStats.loc[genes, "m"].values, g["gene_m_ref"])
+    d2 = Dataset(fn)                                           # cached size factors are re-loaded
+    assert np.array_equal(d2.sf, g["sf_ref"])
+    with pytest.raises(ValueError, match="None of the input genes"):
+        d.get_scaling_params(["NOPE"])
+
+
+@pytest.mark.parametrize("n_dense", [1, 7, 8, 9, 127, 128, 129, 255, 256, 257, 1000, 4099, 20011, 70001])
+def test_sparse_row_stats_follow_numpy_pairwise_order(n_dense):
+    """The device reduction walks NumPy's pairwise tree: sums, means, variances and non-zero means of random
+    sparse rows equal NumPy's float32 results bit for bit at lengths around every split rule (< 8, blocks of
+    128, halves cut at multiples of 8), with dropped columns, empty rows and rows of one value."""
+    import scipy.sparse as sp
+    from nabo_b200 import core
+    from oracle import nabo_oracle as O
+    rng = np.random.default_rng(n_dense)
+    n_rows, n_cols = 37, n_dense + 13
+    dens = rng.random((n_rows, n_cols)) < rng.choice([0.02, 0.3, 0.9], size=(n_rows, 1))
+    dens[0] = False                                            # empty row
+    dens[1] = False; dens[1, n_cols // 2] = True               # one value
+    vals = (rng.gamma(0.7, 40.0, size=(n_rows, n_cols)).astype(np.int64) + 1) * dens
+    csr = sp.csr_matrix(vals.astype(np.float32))
+    csr.sort_indices()
+    keep = np.sort(rng.choice(n_cols, n_dense, replace=False))
+    pos = np.full(n_cols, -1, dtype=np.int32)
+    pos[keep] = np.arange(n_dense, dtype=np.int32)
+    scale = rng.random(n_dense).astype(np.float32) * 3 + 0.01
+    st = core.sparse_row_stats(csr.indptr.astype(np.int64), csr.indices, csr.data, pos, n_dense, scale=scale)
+    dense = vals.astype(np.float32)[:, keep] * scale
+    exp_sum = np.array([r.sum() for r in dense], dtype=np.float32)
+    assert np.array_equal(st["sum"], exp_sum)
+    assert np.array_equal(st["mean"], np.array([r.mean() for r in dense], dtype=np.float32))
+    assert np.array_equal(st["var"], np.array([r.var() for r in dense], dtype=np.float32))
+    assert np.array_equal(st["npos"], (dense > 0).sum(1))
+    nz = np.array([r[r > 0].mean() if (r > 0).any() else 0.0 for r in dense], dtype=np.float32)
+    assert np.array_equal(st["nzmean"], nz)
+    plain = core.sparse_row_stats(csr.indptr.astype(np.int64), csr.indices, csr.data, pos, n_dense, moments=False)
+    assert np.array_equal(plain["sum"], np.array([r.sum() for r in vals.astype(np.float32)[:, keep]], dtype=np.float32))
+    # and the oracle restatement agrees with the same NumPy calls
+    tot = O.size_factor_sums(csr.indptr, csr.indices, csr.data, n_cols, keep)
+    assert np.array_equal(tot, plain["sum"])

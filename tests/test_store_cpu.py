@@ -110,28 +110,28 @@ def test_graph_validation(tmp_path):
         g.get_mapping_score("T")
 
 
-def test_dataset_host_stats_match_reference(tmp_path, golden):
-    """set_sf / set_gene_stats / get_scaling_params are host code: bit-identical mu, sigma, sf."""
-    from nabo_b200.dataset import Dataset, write_dataset
+def test_dataset_stats_restatement_matches_reference(golden):
+    """Oracle restatement of set_sf / set_gene_stats (NumPy float32 reductions) == the unmodified reference."""
+    import scipy.sparse as sp
+    from oracle import nabo_oracle as O
     g = golden("dataset_small")
-    counts = g["counts_ref"].astype(np.int64)
-    genes = ["G%04d" % i for i in range(counts.shape[1])]
-    cells = ["R%04d" % i for i in range(counts.shape[0])]
-    fn = str(tmp_path / "ref.h5")
-    write_dataset(fn, counts, cells, genes)
-    d = Dataset(fn, force_recalc=True)
-    assert d.cells == cells and d.genes == genes
-    d.set_sf()
-    assert np.array_equal(d.sf, g["sf_ref"])
-    d.set_gene_stats()
-    hvg = [genes[i] for i in g["gene_idx"]]
-    sp = d.get_scaling_params(hvg)
-    assert np.array_equal(sp["mu"].values, g["mu"]) and np.array_equal(sp["sigma"].values, g["sigma"])
-    assert np.array_equal(d.geneStats.loc[genes, "m"].values, g["gene_m_ref"])
-    d2 = Dataset(fn)                                           # cached size factors are re-loaded
-    assert np.array_equal(d2.sf, g["sf_ref"])
-    with pytest.raises(ValueError, match="None of the input genes"):
-        d.get_scaling_params(["NOPE"])
+    counts = g["counts_ref"].astype(np.float32)
+    csr = sp.csr_matrix(counts)
+    csr.sort_indices()
+    n_cells, n_genes = counts.shape
+    tot = O.size_factor_sums(csr.indptr, csr.indices, csr.data, n_genes, np.arange(n_genes))
+    tot[tot == 0] = 1
+    sf = (1000.0 / tot).astype(np.float32)
+    assert np.array_equal(sf, g["sf_ref"])
+    csc = csr.tocsc()
+    csc.sort_indices()
+    m, nzm, var, nc = O.gene_stats(csc.indptr, csc.indices, csc.data, n_cells, np.arange(n_cells), sf)
+    valid = nc > 0
+    gm = g["gene_m_ref"]
+    assert np.array_equal(m[valid].astype(np.float64), gm[valid])
+    gi = g["gene_idx"]
+    assert np.array_equal(m[gi].astype(np.float64), g["mu"])
+    assert np.array_equal(np.sqrt(var[gi].astype(np.float64)), g["sigma"])
 
 
 def test_reopen_uses_cached_content_and_notices_foreign_writes(tmp_path):
