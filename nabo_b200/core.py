@@ -246,6 +246,19 @@ def snn_weight_lut(k: int) -> np.ndarray:
     return lut
 
 
+_LUT_DEV: Dict[tuple, "torch.Tensor"] = {}
+
+
+def _lut_dev(k: int, device) -> "torch.Tensor":
+    """Device copy of the weight table, cached: a fresh pageable host->device copy per call would block the
+    host until the stream's earlier kernels have finished and expose every later launch latency."""
+    key = (int(k), str(device))
+    t = _LUT_DEV.get(key)
+    if t is None:
+        t = _LUT_DEV[key] = torch.from_numpy(snn_weight_lut(k)).to(device)
+    return t
+
+
 def fix_weight(k: int) -> float:
     """Default weight of repair edges (nabo/_mapping.py:478-479)."""
     return 0.5 / ((2 * (k - 1)) - 0.5)
@@ -262,7 +275,7 @@ def snn_weights(tgt_knn, ref_knn, k: Optional[int] = None, out=None):
         k = kk
     if k != kk:
         td = td[:, :k].contiguous()
-    lut = _dev(snn_weight_lut(k), torch.float64)
+    lut = _lut_dev(k, td.device)
     if out is not None:
         cnt, w = out
     else:
@@ -284,7 +297,7 @@ def mapping_scores(tgt_knn, counts, n_ref: int, k: Optional[int] = None, include
     td, cd = _dev(tgt_knn, torch.int32), _dev(counts, torch.uint8)
     n, kk = td.shape
     k = kk if k is None else k
-    lut = _dev(snn_weight_lut(k), torch.float64)
+    lut = _lut_dev(k, td.device)
     inc = None
     n_inc = n if n_targets_total is None else int(n_targets_total)
     if include is not None:
@@ -314,7 +327,7 @@ def classify_targets(tgt_knn, counts, ref_labels, n_labels: int, k: Optional[int
     host = _is_host(tgt_knn, counts, ref_labels)
     td, cd, ld = _dev(tgt_knn, torch.int32), _dev(counts, torch.uint8), _dev(ref_labels, torch.int32)
     n, kk = td.shape
-    lut = _dev(snn_weight_lut(kk if k is None else k), torch.float64)
+    lut = _lut_dev(kk if k is None else k, td.device)
     out = torch.empty(n, dtype=torch.int32, device=td.device)
     check(lib().nabo_classify_targets(_ptr(td), _ptr(cd), _ptr(lut), n, kk, _ptr(ld), int(n_labels),
                                       float(weight_frac), int(min_degree), float(min_weight), _ptr(out),

@@ -7,9 +7,10 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------ SNN counts + weights
-// One warp per query.  A = the query's k neighbours, sorted once in shared memory; the k x k_use
-// entries of the neighbours' own kNN rows are spread over the lanes (coalesced row reads) and each
-// is looked up in A by binary search; per-row hit counts accumulate in shared memory.
+// One warp per query.  A = the query's k neighbours, sorted once in shared memory plus a 256-bit
+// signature; one neighbour's own kNN row per iteration, lanes over its entries (one coalesced row read):
+// an entry is binary-searched in A only if the signature admits it, and the row's intersection size
+// is the popcount of the warp's hit ballot (no atomics, no index arithmetic).
 __global__ void __launch_bounds__(256)
 snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int kp2, const int32_t* __restrict__ ref_knn,
            int n_ref, int k_ref, int k_use, const double* __restrict__ lut, uint8_t* __restrict__ counts,
@@ -18,16 +19,24 @@ snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int kp2, con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x * 8 + warp;
     if (t >= n_query) return;
-    int* a_sorted = sm_snn + warp * (2 * kp2 + k);      // [kp2] sorted keys
-    int* a_aux = a_sorted + kp2;                         // [kp2] scratch for the sort (values unused)
-    int* hits = a_aux + kp2;                             // [k]   per-neighbour intersection size
+    int* a_sorted = sm_snn + warp * (2 * kp2 + k + 8);   // [kp2] sorted keys
+    int* a_row = a_sorted + kp2;                         // [kp2] the row in its own order
+    int* hits = a_row + kp2;                             // [k]   per-neighbour intersection size
+    unsigned* bloom = reinterpret_cast<unsigned*>(hits + k);   // 256-bit signature of the row's members
+    if (lane < 8) bloom[lane] = 0u;
     for (int i = lane; i < kp2; i += 32) {
         const int v = i < k ? tgt_knn[(long long)t * k + i] : -1;
         a_sorted[i] = v >= 0 ? v : 0x7fffffff;           // missing neighbours never match
-        a_aux[i] = i;
+        a_row[i] = v;
     }
-    for (int i = lane; i < k; i += 32) hits[i] = 0;
     __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+        const int v = a_row[i];
+        if (v >= 0) {
+            const unsigned h = ((unsigned)v * 2654435761u) >> 24;
+            atomicOr(&bloom[h >> 5], 1u << (h & 31));
+        }
+    }
     // bitonic sort of the keys (ascending)
     for (int size = 2; size <= kp2; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -39,19 +48,39 @@ snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int kp2, con
             }
             __syncwarp();
         }
-    const int total = k * k_use;
-    for (int e = lane; e < total; e += 32) {
-        const int row = e / k_use, col = e - row * k_use;
-        const int j = tgt_knn[(long long)t * k + row];
-        if (j < 0 || j >= n_ref) continue;
-        const int b = ref_knn[(long long)j * k_ref + col];
-        if (b < 0) continue;
-        int lo = 0, hi = kp2;                            // first position with a_sorted[pos] >= b
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (a_sorted[mid] < b) lo = mid + 1; else hi = mid;
+    // one neighbour row per iteration, lanes over its entries (one coalesced row read); an entry is looked up
+    // in the sorted row only if the signature says it may be a member (~1 in 9 of the non-members)
+    // (the gathers of 16 rows are issued back to back before any of them is consumed: the kernel is bound by
+    // L2 latency, not by arithmetic)
+    for (int c0 = 0; c0 < k_use; c0 += 32) {
+        const int col = c0 + lane;
+        for (int r0 = 0; r0 < k; r0 += 16) {
+            int bv[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int row = r0 + u;
+                const int j = row < k ? a_row[row] : -1;
+                bv[u] = (j >= 0 && j < n_ref && col < k_use) ? __ldg(ref_knn + (long long)j * k_ref + col) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int b = bv[u];
+                bool hit = false;
+                if (b >= 0) {
+                    const unsigned h = ((unsigned)b * 2654435761u) >> 24;
+                    if ((bloom[h >> 5] >> (h & 31)) & 1u) {
+                        int lo = 0, hi = kp2;            // first position with a_sorted[pos] >= b
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (a_sorted[mid] < b) lo = mid + 1; else hi = mid;
+                        }
+                        hit = lo < kp2 && a_sorted[lo] == b;
+                    }
+                }
+                const int cnt = __popc(__ballot_sync(0xffffffffu, hit));
+                if (lane == 0 && r0 + u < k) hits[r0 + u] = (c0 == 0 ? 0 : hits[r0 + u]) + cnt;
+            }
         }
-        if (lo < kp2 && a_sorted[lo] == b) atomicAdd(&hits[row], 1);
     }
     __syncwarp();
     for (int i = lane; i < k; i += 32) {
@@ -72,7 +101,7 @@ extern "C" int nabo_snn_weights(const int32_t* tgt_knn, int n_query, int k, cons
     int k_use = k < k_ref ? k : k_ref;   // ref_data[ref_c][:k], _mapping.py:193
     int kp2 = nabo_next_pow2(k);
     if (kp2 < 2) kp2 = 2;
-    snn_kernel<<<(n_query + 7) / 8, 256, 8 * (2 * kp2 + k) * sizeof(int), (cudaStream_t)stream>>>(
+    snn_kernel<<<(n_query + 7) / 8, 256, 8 * (2 * kp2 + k + 8) * sizeof(int), (cudaStream_t)stream>>>(
         tgt_knn, n_query, k, kp2, ref_knn, n_ref, k_ref, k_use, lut, out_counts, out_weights);
     NABO_LAUNCH_CHECK("snn_kernel");
     return 0;
