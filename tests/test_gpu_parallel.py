@@ -51,9 +51,11 @@ qlo, qhi, ri, rd = P.knn_reference_sharded(rt, rt[lo:hi].contiguous(), lo, k, "e
 tlo, thi = P.shard_bounds(len(tgt), world, rank)
 a = P.map_targets_sharded(tt[tlo:thi].contiguous(), rt, ri, k, len(tgt), metric="euclidean")
 b = P.map_reference_sharded(tt, rt[lo:hi].contiguous(), lo, len(ref), ri, k, metric="euclidean")
+c = P.map_reference_sharded(tt, rt[lo:hi].contiguous(), lo, len(ref), ri, k, metric="mod_canberra", dist_factor=0.25)
 np.savez(os.path.join(sys.argv[2], "r%d.npz" % rank), ref_knn=ri.cpu().numpy(), ref_dst=rd.cpu().numpy(),
          a_idx=a["idx"].cpu().numpy(), a_dist=a["dist"].cpu().numpy(), a_sc=a["scores"].cpu().numpy(),
-         b_lo=b["lo"], b_idx=b["idx"].cpu().numpy(), b_dist=b["dist"].cpu().numpy(), b_sc=b["scores"].cpu().numpy())
+         b_lo=b["lo"], b_idx=b["idx"].cpu().numpy(), b_dist=b["dist"].cpu().numpy(), b_sc=b["scores"].cpu().numpy(),
+         c_idx=c["idx"].cpu().numpy(), c_dist=c["dist"].cpu().numpy(), c_sc=c["scores"].cpu().numpy())
 dist.destroy_process_group()
 '''
 
@@ -87,3 +89,11 @@ def test_two_ranks_nccl(tmp_path):
     assert np.array_equal(np.concatenate([r["a_idx"] for r in res]), ti)
     assert np.array_equal(np.concatenate([r["b_idx"] for r in res]), ti)
     assert np.array_equal(np.concatenate([r["b_dist"] for r in res]), td)
+    # modified Canberra (bit-sliced candidate pass per shard), reference-sharded == unsharded exact engine
+    ci, cd = core.knn(tgt, ref, k, "mod_canberra", 0.25, mode="exact")
+    ccnt, _ = core.snn_weights(ci, ri, k)
+    csc = core.mapping_scores(ci, ccnt, len(ref), k)
+    assert np.array_equal(np.concatenate([r["c_idx"] for r in res]), ci)
+    assert np.array_equal(np.concatenate([r["c_dist"] for r in res]), cd)
+    for r in res:
+        np.testing.assert_allclose(r["c_sc"], csc, rtol=1e-12)
