@@ -48,7 +48,9 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
         char* extra = ar.take<char>(cb_extra_bytes(n_query, n_ref, g));
         if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
         NABO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
-        const bool sliced = nabo_cbs_supported(g, k, drop_first);
+        // the interval ends of the sliced pass carry a 1e-6 relative margin over f|x|; it must dominate the FP64
+        // rounding of x -+ f|x| (~1e-16 |x|), so a vanishing dist_factor goes to the FP16 two-phase pass instead
+        const bool sliced = nabo_cbs_supported(g, k, drop_first) && f >= 1e-6;
         int rc = sliced
                      ? nabo_cbs_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, rt, extra,
                                            cb_extra_bytes(n_query, n_ref, g), cand, tau, st)

@@ -173,6 +173,8 @@ def test_canberra_threshold_adversarial(core, f):
     (700, 9000, 64, 20, 0.25),         # past it: FP16 two-phase pass
     (300, 3000, 80, 8, 2.0),           # g > 64: exact engine; f > 1 (intervals straddle zero)
     (300, 3000, 40, 8, 2.0),
+    (300, 3000, 20, 8, 1e-9),          # vanishing dist_factor: FP16 two-phase pass (margin of the sliced pass too thin)
+    (300, 3000, 20, 8, 1e-4),
 ])
 def test_canberra_sliced_shapes(core, n, m, g, k, f):
     """Bit-sliced Canberra pass (bin planes + carry-save count + FP32 evaluation): same result as the exact
@@ -184,7 +186,7 @@ def test_canberra_sliced_shapes(core, n, m, g, k, f):
     fi, fd, st = core.knn(q, r, k, "mod_canberra", f, mode="fast", return_stats=True)
     ei, ed = core.knn(q, r, k, "mod_canberra", f, mode="exact")
     assert same_bits(fd, ed) and np.array_equal(fi, ei)
-    if g <= 64:                          # wider inputs run on the exact engine by design
+    if g <= 64 and f >= 1e-6:            # wider inputs / vanishing f (every pair ties at d = g) run on the exact engine
         assert st["rows_exact_fallback"] <= max(2, n // 50)
 
 
