@@ -77,15 +77,15 @@ constexpr int NT = 256;         // threads: 16 x 16, each owns a 4 x 4 micro til
 constexpr int LDS_T = TQ + 2;   // padded row stride of the k-major tiles (keeps 16 B alignment)
 
 __device__ __forceinline__ void load_tile_kmajor(double* s, const double* __restrict__ src, int ld,
-                                                 int row0, int nrows, int g, const int* row_ids) {
-    // s[k * LDS_T + r] = src[row(row0 + r)][k]; rows past nrows are zero-filled
+                                                 int row0, int nrows, int g, const int* row_ids, int k0 = 0) {
+    // s[k * LDS_T + r] = src[row(row0 + r)][k0 + k], k < g; rows past nrows are zero-filled
     for (int e = threadIdx.x; e < TQ * g; e += NT) {
         int r = e / g, k = e - r * g;
         int row = row0 + r;
         double v = 0.0;
         if (row < nrows) {
             long long rr = row_ids ? row_ids[row] : row;
-            v = src[rr * (long long)ld + k];
+            v = src[rr * (long long)ld + k0 + k];
         }
         s[k * LDS_T + r] = v;
     }
@@ -237,9 +237,12 @@ __global__ void __launch_bounds__(NT, 1)
 knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ r, int ldr, int n_query,
                  int n_ref, int g, int k, double f, const uint8_t* __restrict__ mask, int drop_first,
                  int idx_offset, const int* __restrict__ row_ids, const int* __restrict__ n_rows_dev,
-                 int cap, const NaboExactSplit sp, int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+                 int cap, int gc, const NaboExactSplit sp, int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    // gc = dimensions per shared-memory tile chunk (gc == g: the whole vectors, query tile loaded once; gc < g:
+    // both tiles are streamed in chunks, the accumulators carry over - same sequential order of additions)
     extern __shared__ double smem[];
-    const ExactSmem s = carve_exact(smem, g, cap);
+    const ExactSmem s = carve_exact(smem, gc, cap);
+    const bool chunked = gc < g;
     const int nq_total = n_rows_dev ? *n_rows_dev : n_query;   // fallback mode: row list on device
     // fallback for FEW rows: the reference range is split over blockIdx.y and the partial lists are
     // merged afterwards (mode 1); with many rows the plain row-parallel kernel is used (mode 2)
@@ -256,47 +259,62 @@ knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tr = threadIdx.x & 15, tq = threadIdx.x >> 4;
 
-    load_tile_kmajor(s.xs, q, ldq, q0, nq_total, g, row_ids);
     if (threadIdx.x < TQ) {
         s.cnt[threadIdx.x] = 0;
         s.tau_d[threadIdx.x] = CUDART_INF;
         s.tau_i[threadIdx.x] = 0x7fffffff;
     }
-    __syncthreads();
-    if (METRIC == NABO_COSINE && threadIdx.x < TQ) {
-        double acc = 0.0;
-        for (int kk = 0; kk < g; ++kk) { double v = s.xs[kk * LDS_T + threadIdx.x]; acc = __dadd_rn(acc, __dmul_rn(v, v)); }
-        s.nq[threadIdx.x] = acc;
+    if (!chunked) {
+        load_tile_kmajor(s.xs, q, ldq, q0, nq_total, g, row_ids);
+        __syncthreads();
+        if (METRIC == NABO_COSINE && threadIdx.x < TQ) {
+            double acc = 0.0;
+            for (int kk = 0; kk < g; ++kk) { double v = s.xs[kk * LDS_T + threadIdx.x]; acc = __dadd_rn(acc, __dmul_rn(v, v)); }
+            s.nq[threadIdx.x] = acc;
+        }
+    } else if (METRIC == NABO_COSINE) {
+        double acc = 0.0;                                   // squared norm of the queries, chunk by chunk, same order
+        for (int kc = 0; kc < g; kc += gc) {
+            const int gn = min(gc, g - kc);
+            __syncthreads();
+            load_tile_kmajor(s.xs, q, ldq, q0, nq_total, gn, row_ids, kc);
+            __syncthreads();
+            if (threadIdx.x < TQ)
+                for (int kk = 0; kk < gn; ++kk) { double v = s.xs[kk * LDS_T + threadIdx.x]; acc = __dadd_rn(acc, __dmul_rn(v, v)); }
+        }
+        if (threadIdx.x < TQ) s.nq[threadIdx.x] = acc;
     }
 
     for (int r0 = r_lo; r0 < r_hi; r0 += TR) {
-        __syncthreads();   // previous tile fully consumed (and compaction finished)
-        load_tile_kmajor(s.ys, r, ldr, r0, r_hi, g, nullptr);
-        __syncthreads();
-        if (METRIC == NABO_COSINE) {
-            if (threadIdx.x < TR) {
-                double acc = 0.0;
-                for (int kk = 0; kk < g; ++kk) { double v = s.ys[kk * LDS_T + threadIdx.x]; acc = __dadd_rn(acc, __dmul_rn(v, v)); }
-                s.nr[threadIdx.x] = acc;
-            }
-            __syncthreads();
-        }
         double acc[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-        for (int kk = 0; kk < g; ++kk) {
-            double xv[4], yv[4];
+        for (int kc = 0; kc < g; kc += gc) {
+            const int gn = min(gc, g - kc);
+            __syncthreads();   // previous tile / chunk fully consumed (and compaction finished)
+            if (chunked) load_tile_kmajor(s.xs, q, ldq, q0, nq_total, gn, row_ids, kc);
+            load_tile_kmajor(s.ys, r, ldr, r0, r_hi, gn, nullptr, kc);
+            __syncthreads();
+            if (METRIC == NABO_COSINE && threadIdx.x < TR) {
+                double nacc = kc == 0 ? 0.0 : s.nr[threadIdx.x];
+                for (int kk = 0; kk < gn; ++kk) { double v = s.ys[kk * LDS_T + threadIdx.x]; nacc = __dadd_rn(nacc, __dmul_rn(v, v)); }
+                s.nr[threadIdx.x] = nacc;
+            }
+            for (int kk = 0; kk < gn; ++kk) {
+                double xv[4], yv[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) xv[a] = s.xs[kk * LDS_T + tq * 4 + a];
+                for (int a = 0; a < 4; ++a) xv[a] = s.xs[kk * LDS_T + tq * 4 + a];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) yv[b] = s.ys[kk * LDS_T + tr * 4 + b];
+                for (int b = 0; b < 4; ++b) yv[b] = s.ys[kk * LDS_T + tr * 4 + b];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = Pair<METRIC>::step(acc[a][b], xv[a], yv[b], f);
+                    for (int b = 0; b < 4; ++b) acc[a][b] = Pair<METRIC>::step(acc[a][b], xv[a], yv[b], f);
+            }
         }
+        if (METRIC == NABO_COSINE) __syncthreads();        // reference norms complete
         // filter against the running k-th best and append survivors
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -479,13 +497,16 @@ int nabo_knn_exact_launch_ex(const double* q, int ldq, const double* r, int ldr,
     NABO_ARG(g >= 1, "knn: g=%d", g);
     if (n_query == 0) return 0;
     const int cap = exact_cap_for(ksel);
-    size_t smem = exact_smem_bytes(g, cap);
+    // whole vectors in shared memory when they fit next to the candidate buffers, else chunks of gc dimensions
+    int gc = g;
+    while (gc > 8 && exact_smem_bytes(gc, cap) > (size_t)227 * 1024) gc = (gc + 1) / 2;
+    size_t smem = exact_smem_bytes(gc, cap);
     NABO_ARG(smem <= 227 * 1024, "knn: g=%d with k=%d needs %zu B of shared memory (max 232448)", g, k, smem);
     dim3 grid((n_query + TQ - 1) / TQ, sp.mode == 1 ? sp.nsplit : 1);
 #define LAUNCH(M)                                                                                         \
     NABO_CUDA(cudaFuncSetAttribute(knn_exact_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     knn_exact_kernel<M><<<grid, NT, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, \
-                                                idx_offset, row_ids, n_rows_dev, cap, sp, out_idx, out_dist);
+                                                idx_offset, row_ids, n_rows_dev, cap, gc, sp, out_idx, out_dist);
     if (metric == NABO_EUCLIDEAN) { LAUNCH(NABO_EUCLIDEAN) }
     else if (metric == NABO_MOD_CANBERRA) { LAUNCH(NABO_MOD_CANBERRA) }
     else if (metric == NABO_COSINE) { LAUNCH(NABO_COSINE) }
