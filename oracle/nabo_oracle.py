@@ -226,24 +226,27 @@ def snn_weights(target_knn, ref_knn, k: int | None = None):
 def mapping_scores(target_knn, weights, n_ref: int, n_targets: int | None = None,
                    min_weight: float = 0.0, min_score: float = 0.0,
                    weighted: bool = True, score_multiplier: float = 1000.0,
-                   include: np.ndarray | None = None) -> np.ndarray:
+                   include: np.ndarray | None = None, counts=None) -> np.ndarray:
     """nabo/_graph.py:643-653, 690-693.
 
     score[r] = score_multiplier * sum_{t in include, edge (r,t), w > min_weight} w
                / len(include)          (weighted)
              = score_multiplier * #edges / len(include)   (unweighted)
-    then zeroed below min_score.  Edges exist where weight > 0 (snn > 0,
-    _mapping.py:195).  Summation follows target order (adjacency insertion
+    then zeroed below min_score.  An edge exists where snn > 0 (_mapping.py:195):
+    pass ``counts`` to say so exactly; without it a non-zero weight stands for an
+    edge (wrong only where round() gives 0.0 for snn > 0, k >= 102; note that k = 1
+    yields the weight -1).  Summation follows target order (adjacency insertion
     order of the reference)."""
     target_knn = np.asarray(target_knn)
     weights = np.asarray(weights, dtype=np.float64)
+    edge = (np.asarray(counts) > 0) if counts is not None else (weights != 0)
     n = target_knn.shape[0]
     rows = np.arange(n) if include is None else np.asarray(include)
     denom = len(rows) if n_targets is None else n_targets
     acc = np.zeros(n_ref, dtype=np.float64)
     for t in rows:
-        for j, w in zip(target_knn[t], weights[t]):
-            if w > 0:                       # an edge exists
+        for j, w, e in zip(target_knn[t], weights[t], edge[t]):
+            if e:                           # an edge exists
                 if weighted:
                     if w > min_weight:
                         acc[j] += w
@@ -255,7 +258,7 @@ def mapping_scores(target_knn, weights, n_ref: int, n_targets: int | None = None
 
 def classify_targets(target_knn, weights, ref_labels, n_labels: int,
                      weight_frac: float = 0.5, min_degree: int = 2,
-                     min_weight: float = 0.0):
+                     min_weight: float = 0.0, counts=None):
     """nabo/_graph.py:722-792 (classify_target), array form.  For each target
     node: degree (= number of edges, weight > 0) < min_degree -> -1 (na_label);
     edges with weight > min_weight vote their weight for the reference node's
@@ -265,14 +268,15 @@ def classify_targets(target_knn, weights, ref_labels, n_labels: int,
     iteration order (unspecified); here the lowest label wins."""
     target_knn = np.asarray(target_knn)
     weights = np.asarray(weights, dtype=np.float64)
+    edge = (np.asarray(counts) > 0) if counts is not None else (weights != 0)     # as in mapping_scores
     n = target_knn.shape[0]
     out = np.full(n, -1, dtype=np.int64)
     for t in range(n):
         votes = np.zeros(n_labels, dtype=np.float64)
         deg = 0
         tot = 0.0
-        for j, w in zip(target_knn[t], weights[t]):
-            if w > 0:
+        for j, w, e in zip(target_knn[t], weights[t], edge[t]):
+            if e:
                 deg += 1
                 if w > min_weight and ref_labels[j] >= 0:
                     votes[ref_labels[j]] += w

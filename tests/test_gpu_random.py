@@ -73,3 +73,82 @@ def test_random_self_knn_case(core, seed):
     if len(r) <= 1000:
         oi, od = O.knn(r, r, k, metric, c["f"], drop_first=True)
         assert same_bits(ed, od) and np.array_equal(ei, oi)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_graph_ops(core, seed):
+    """SNN counts / weights, mapping scores (all keyword variants), cluster vote and shard merge on random
+    index tables of random shape against the oracle."""
+    rng = np.random.default_rng(5000 + seed)
+    m = int(rng.choice([40, 257, 1000, 5003]))
+    n = int(rng.choice([1, 33, 500, 2000]))
+    k = int(min(rng.choice([1, 3, 10, 30, 31, 33, 64, 100]), m - 1))
+    if k == 2:
+        k = 3                                                   # k = 2 raises ZeroDivisionError upstream
+    k_ref = int(min(rng.choice([k, k, max(1, k - 2), k + 5]), m - 1))
+    near = rng.random() < 0.5                                   # neighbours drawn from a window: many shared ones
+    def table(rows, width):
+        out = np.empty((rows, width), dtype=np.int32)
+        for i in range(rows):
+            pool = (np.arange(width * 3) + rng.integers(0, m)) % m if near else np.arange(m)
+            out[i] = rng.choice(pool, width, replace=False)
+        return out
+    tk, rk = table(n, k), table(m, k_ref)
+    cnt, w = core.snn_weights(tk, rk, k)
+    ocnt, ow = O.snn_weights(tk, rk[:, :min(k, k_ref)], k)
+    assert np.array_equal(cnt, ocnt) and np.array_equal(w, ow)
+    for kw in (dict(), dict(min_weight=float(np.median(w[w > 0])) if (w > 0).any() else 0.0), dict(weighted=False),
+               dict(min_score=5.0), dict(score_multiplier=1.0),
+               dict(include=np.sort(rng.choice(n, max(1, n // 3), replace=False)))):
+        got = core.mapping_scores(tk, cnt, m, k, **kw)
+        exp = O.mapping_scores(tk, w, m, counts=cnt, **kw)
+        np.testing.assert_allclose(got, exp, rtol=1e-12, atol=0)
+    n_labels = int(rng.choice([1, 3, 17]))
+    labels = rng.integers(-1, n_labels, size=m).astype(np.int32)
+    for kw in (dict(), dict(weight_frac=0.2, min_degree=1, min_weight=0.0), dict(min_degree=5, min_weight=float(w.max()) / 2)):
+        got = core.classify_targets(tk, cnt, labels, n_labels, k, **kw)
+        full = dict(weight_frac=0.5, min_degree=2, min_weight=0.1)
+        full.update(kw)
+        exp = O.classify_targets(tk, w, labels, n_labels, counts=cnt, **full)
+        assert np.array_equal(got, exp)
+    shards = int(rng.choice([1, 2, 3, 8]))
+    si = rng.integers(0, 10 * m, size=(shards, n, k)).astype(np.int32)
+    sd = np.round(rng.random((shards, n, k)) * 4, 1)            # coarse values: ties across shards
+    sd[rng.random(sd.shape) < 0.05] = np.nan
+    order = np.argsort(np.where(np.isnan(sd), np.inf, sd), axis=2, kind="stable")      # shards arrive sorted
+    si, sd = np.take_along_axis(si, order, 2), np.take_along_axis(sd, order, 2)
+    mi, md = core.merge_topk(si, sd)
+    oi, od = O.merge_topk(list(si), list(sd), k)
+    assert np.array_equal(md, od, equal_nan=True)
+    ok = ~np.isnan(od)
+    assert np.array_equal(mi[ok], oi[ok])
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_projection(core, seed):
+    """Scaling + projection from dense and CSR counts with missing genes, random sizes."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.choice([1, 33, 700]))
+    n_genes = int(rng.choice([50, 333, 2000]))
+    G = int(min(rng.choice([7, 64, 500]), n_genes))
+    C = int(min(rng.choice([1, 25, 50, 100]), G))
+    counts = (rng.gamma(0.3, 8.0, size=(n, n_genes)) * (rng.random((n, n_genes)) < 0.2)).astype(np.int64).astype(np.float32)
+    sf = (1000.0 / np.maximum(counts.sum(1), 1)).astype(np.float32)
+    gi = rng.choice(n_genes, G, replace=False).astype(np.int32)
+    missing = rng.random(G) < 0.1
+    mu, sg = rng.random(G) + 0.05, rng.random(G) + 0.3
+    comps, mean = rng.normal(size=(C, G)), rng.normal(size=G)
+    gi_m = np.where(missing, -1, gi).astype(np.int32)
+    dense = counts[:, gi].copy()
+    dense[:, missing] = 0.0
+    exp = O.project(dense, sf, mu, sg, comps, mean)
+    tol = 1e-11 * max(1.0, np.abs(exp).max())
+    np.testing.assert_allclose(core.project(counts, gi_m, sf, mu, sg, comps, mean), exp, rtol=0, atol=tol)
+    csr = sp.csr_matrix(counts)
+    csr.sort_indices()
+    pos = np.full(n_genes, -1, dtype=np.int32)
+    pos[gi[~missing]] = np.nonzero(~missing)[0].astype(np.int32)
+    got = core.project_csr(csr.indptr.astype(np.int64), csr.indices.astype(np.int32), csr.data.astype(np.float32), pos,
+                           sf, mu, sg, comps, mean)
+    np.testing.assert_allclose(got, exp, rtol=0, atol=tol)
