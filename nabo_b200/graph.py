@@ -220,7 +220,7 @@ class Graph(nx.Graph):
             vals = _scores_from_weights(s.knn, s.weights, m, mask, min_weight, weighted, score_multiplier)
         if verbose:
             deg = np.zeros(m, dtype=np.int64)
-            valid = (s.knn >= 0) & ((s.snn > 0) if s.snn is not None else (s.weights > 0)) & (mask[:, None] > 0)
+            valid = (s.knn >= 0) & ((s.snn > 0) if s.snn is not None else (s.knn >= 0)) & (mask[:, None] > 0)
             np.add.at(deg, s.knn[valid], 1)
             print("INFO: The bipartite graph has %d edges" % int(valid.sum()))
             print("INFO: Mapping calculated against %d %s nodes" % (len(include), target))
@@ -329,7 +329,7 @@ class Graph(nx.Graph):
         if s.snn is not None:
             cnt = (s.snn > 0).astype(np.uint8)
         else:
-            cnt = (s.weights > 0).astype(np.uint8)
+            cnt = (s.knn >= 0).astype(np.uint8)
         indptr, indices = self._ref_csr()
         mean, connected = core.mapping_specificity(indptr, indices, s.knn, cnt)
         if not bool(np.all(connected)):
@@ -346,7 +346,7 @@ class Graph(nx.Graph):
         """nabo/_graph.py:826-857: mean specificity of the target nodes mapped to each reference node
         (adjacency order = target order, as upstream)."""
         s = self._samples[target]
-        mask = (s.snn > 0) if s.snn is not None else (s.weights > 0)
+        mask = (s.snn > 0) if s.snn is not None else (s.knn >= 0)
         rows, cols = np.nonzero(mask)
         refs = s.knn[rows, cols]
         order = np.argsort(refs, kind="stable")             # per reference node: its targets in target order
@@ -369,12 +369,13 @@ class Graph(nx.Graph):
 
 def _scores_from_weights(knn, weights, n_ref, mask, min_weight, weighted, mult):
     """Per-node-layout graphs carry weights, not SNN counts: map weight -> rank table -> GPU kernel."""
-    vals = np.unique(weights[weights > 0])
+    exists = knn >= 0                                   # an edge is an entry of the node's dataset, whatever its weight
+    vals = np.unique(weights[exists])
     lut = np.concatenate([[0.0], vals])
     if len(lut) > 255:
         raise ValueError("ERROR: more than 254 distinct edge weights; store the graph in the columnar layout")
-    cnt = np.searchsorted(vals, weights).astype(np.uint8) + 1
-    cnt[weights <= 0] = 0
+    cnt = (np.searchsorted(vals, weights) + 1).astype(np.uint8)
+    cnt[~exists] = 0
     import torch
     from . import _lib
     import ctypes as C
