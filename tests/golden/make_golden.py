@@ -126,7 +126,7 @@ def golden_kernels(nabo, out):
 
 # ---------------------------------------------------------------- B: mapping
 def run_mapping(nabo, tmp, ref, tgt, ref_names, tgt_names, use_comps, k, f, chunk,
-                ignore=None, tag="m"):
+                ignore=None, tag="m", specificity=True):
     ref_fn = os.path.join(tmp, tag + "_ref_pca.h5")
     tgt_fn = os.path.join(tmp, tag + "_tgt_pca.h5")
     map_fn = os.path.join(tmp, tag + "_map.h5")
@@ -172,6 +172,8 @@ def run_mapping(nabo, tmp, ref, tgt, ref_names, tgt_names, use_comps, k, f, chun
                      ("score_minscore", dict(min_score=2.0))):
         sc = g.get_mapping_score("TGT", **kw)
         res[name] = np.array([sc[n + "_REF"] for n in sref], dtype=np.float64)
+    if not specificity:
+        return res
     # mapping specificity (nabo/_graph.py:794-857): raw (NaN kept), NaN-filled, and folded back on the reference
     with np.errstate(all="ignore"), warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -203,6 +205,27 @@ def golden_mapping(nabo, out, tmp):
     np.savez_compressed(os.path.join(out, "mapping_ignore.npz"), use_comps=20, k=5, f=0.5, mask=mask,
                         **base, **res)
     print("mapping_ignore.npz written")
+
+
+def golden_mapping_edge(nabo, out, tmp):
+    """Edge semantics of the reference itself: more neighbours asked for than there are un-ignored reference
+    cells, a target with a NaN coordinate, targets far outside the reference (every Canberra term saturates:
+    d == use_comps for all references, one big tie class), an all-zero target."""
+    ref = synth.pc_mixture(60, 12, seed=3, n_clusters=3)
+    tgt = synth.pc_mixture(40, 12, seed=103, n_clusters=3)
+    tgt[3, 5] = np.nan
+    tgt[4] = 1e6 * (1.0 + np.arange(12))             # saturates every dimension against every reference cell
+    tgt[5] = -tgt[4]
+    tgt[6] = 0.0                                     # |x - y| < f|x| is never true for x = 0
+    rn, tn = synth.cell_names(60, "R"), synth.cell_names(40, "T")
+    ign = [rn[i] for i in range(60) if i % 10 != 0]  # 6 reference cells left, k = 8 asked for
+    res = run_mapping(nabo, tmp, ref, tgt, rn, tn, use_comps=10, k=8, f=0.25, chunk=16, ignore=ign, tag="e1",
+                      specificity=False)
+    mask = np.ones(60, dtype=bool)
+    mask[::10] = False
+    np.savez_compressed(os.path.join(out, "mapping_edge.npz"), use_comps=10, k=8, f=0.25, mask=mask, ref=ref, tgt=tgt,
+                        **res)
+    print("mapping_edge.npz written")
 
 
 # ---------------------------------------------------------------- C: dataset
@@ -276,12 +299,14 @@ def golden_c1(nabo, out, tmp):
 
 if __name__ == "__main__":
     nabo = install_shims()
-    which = sys.argv[1:] or ["kernels", "mapping", "dataset", "c1"]
+    which = sys.argv[1:] or ["kernels", "mapping", "edge", "dataset", "c1"]
     with tempfile.TemporaryDirectory() as tmp:
         if "kernels" in which:
             golden_kernels(nabo, HERE)
         if "mapping" in which:
             golden_mapping(nabo, HERE, tmp)
+        if "edge" in which:
+            golden_mapping_edge(nabo, HERE, tmp)
         if "dataset" in which:
             golden_dataset(nabo, HERE, tmp)
         if "c1" in which:

@@ -244,3 +244,41 @@ def test_sparse_row_stats_follow_numpy_pairwise_order(n_dense):
     # and the oracle restatement agrees with the same NumPy calls
     tot = O.size_factor_sums(csr.indptr, csr.indices, csr.data, n_cols, keep)
     assert np.array_equal(tot, plain["sum"])
+
+
+def test_mapping_edge_semantics(tmp_path, golden):
+    """The reference's own behaviour at the edges (golden mapping_edge): more neighbours asked for than there are
+    un-ignored reference cells (ignored cells fill the tail of the row - which ones is unspecified upstream, they
+    sort as NaN), a NaN coordinate in a target (that term counts 1), targets whose every term saturates
+    (d == use_comps for every reference cell: one tie class) and an all-zero target."""
+    from nabo_b200 import Mapping, store, synth
+    g = golden("mapping_edge")
+    uc, k, f = int(g["use_comps"]), int(g["k"]), float(g["f"])
+    ref, tgt, mask = g["ref"], g["tgt"], g["mask"]
+    rn, tn = synth.cell_names(len(ref), "R"), synth.cell_names(len(tgt), "T")
+    ref_fn, tgt_fn, map_fn = (str(tmp_path / x) for x in ("ref.h5", "tgt.h5", "map.h5"))
+    _write_pca(ref_fn, rn, ref)
+    _write_pca(tgt_fn, tn, tgt)
+    m = Mapping(map_fn, "REF", ref_fn, "data", overwrite=True)
+    m.set_parameters(uc, k, f, 16)
+    m.make_ref_graph()
+    m.map_target("TGT", tgt_fn, "data", ignore_ref_cells=[rn[i] for i in np.nonzero(mask)[0]])
+    h5 = store.File(map_fn, "r")
+    ruid = h5["name_stash/ref_name"][1].decode()
+    tuid = [i[1].decode() for i in h5["name_stash/target_names"] if i[0] == b"TGT"][0]
+    rk = np.array([h5[ruid + "_sortedDist"][c][:k] for c in rn])
+    rd = np.array([h5[ruid + "_dist"][c][:k] for c in rn])
+    tk = np.array([h5[tuid + "_sortedDist"][c][:k] for c in tn])
+    td = np.array([h5[tuid + "_dist"][c][:k] for c in tn])
+    h5.close()
+    n_live = int((~mask).sum())
+    assert n_live < k
+    gt = g["tgt_sorted_full"][:, :n_live].astype(np.int64)
+    assert O.tie_classes_equal(tk[:, :n_live], td[:, :n_live], gt, np.take_along_axis(g["tgt_dist_full"], gt, 1))
+    assert not mask[tk[:, :n_live]].any()
+    assert mask[tk[:, n_live:]].all() and np.isnan(td[:, n_live:]).all()      # ignored cells fill the tail, as upstream
+    assert mask[g["tgt_sorted_full"][:, n_live:k]].all()
+    for t in (4, 5, 6):                                                       # saturated rows: every distance == use_comps
+        assert (td[t, :n_live] == uc).all()
+    gr = g["ref_sorted_full"][:, :k].astype(np.int64)
+    assert O.tie_classes_equal(rk, rd, gr, np.take_along_axis(g["ref_dist_full"], gr, 1), head_truncated=True)

@@ -215,3 +215,18 @@ def test_mapping_specificity_matches_reference(golden, name):
     assert np.array_equal(np.isnan(got), np.isnan(exp))
     assert np.array_equal(got[~np.isnan(exp)], exp[~np.isnan(exp)])
     assert np.isnan(exp).sum() == (cnt.sum(1) < 2).sum()
+
+
+def test_edge_semantics_of_the_reference(golden):
+    """Oracle kNN on the reference's edge cases (golden mapping_edge): ignored cells fill the tail of a row when
+    k exceeds the live cells, NaN coordinates count as saturated terms, fully saturated rows tie at use_comps."""
+    g = golden("mapping_edge")
+    uc, k, f, mask = int(g["use_comps"]), int(g["k"]), float(g["f"]), g["mask"]
+    n_live = int((~mask).sum())
+    oi, od = O.knn(g["tgt"][:, :uc], g["ref"][:, :uc], k, "mod_canberra", f, mask=mask)
+    gt = g["tgt_sorted_full"][:, :n_live].astype(np.int64)
+    assert O.tie_classes_equal(oi[:, :n_live], od[:, :n_live], gt, np.take_along_axis(g["tgt_dist_full"], gt, 1))
+    assert mask[oi[:, n_live:]].all() and np.isnan(od[:, n_live:]).all()
+    assert (od[[4, 5, 6], :n_live] == uc).all()
+    full = O.mod_canberra_dist(g["tgt"][:, :uc], g["ref"][:, :uc], f)
+    assert np.array_equal(full, g["tgt_dist_full"])          # incl. the NaN-coordinate target and the zero target
