@@ -289,7 +289,10 @@ def run_b200_refshard(a):
     line = {
         "metric": "target_cells_mapped_per_s", "value": N / (ms_step / 1e3), "unit": "cells/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64 (candidates: f16x2-split tcgen05, f32 accumulate)", "data": "synthetic",
+        "vs_baseline": None,
+        "dtype": ("f64 (candidates: f16x2-split tcgen05, f32 accumulate)" if a.metric != "mod_canberra" else
+                  "f64 (candidates: bit-sliced u32 count bound, f32 evaluation)"),
+        "data": "synthetic",
         "config": {"workload": "config4-shaped: %d targets x %d reference cells (%d rows per GPU), %d PCs, k=%d, %s"
                                % (N, m_total, M, g, k, a.metric),
                    "engine": a.engine, "sharding": "reference rows; all_gather_into_tensor of (idx, dist) + nabo_merge_topk; "
