@@ -26,8 +26,6 @@
 #include "ptx.cuh"
 #include "select.cuh"
 
-#include <stdlib.h>
-
 namespace cbs {
 
 using namespace sel;   // make_key, compact_select, compact_sort_inline
@@ -506,8 +504,6 @@ sliced_kernel(const Params p) {
 
 // ------------------------------------------------------------------ host side
 bool nabo_cbs_supported(int g, int k, int drop_first) {
-    const char* legacy = getenv("NABO_CB_LEGACY");
-    if (legacy && legacy[0] == '1') return false;
     if (g < 1 || g > 64) return false;
     const int ksel = k + (drop_first ? 1 : 0);
     return cbs::plan_smem(g).stages >= 2 && ksel + 8 <= cbs::CAP - 64;
