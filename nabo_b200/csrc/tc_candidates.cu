@@ -181,9 +181,10 @@ struct Params {
     const __half* qa;       // packed queries  [n_qtiles_padded][TILE*kp]
     const __half* rb;       // packed references [n_rtiles][TILE*kp]
     int n_query, n_ref, kp, n_items, n_rtiles, stages, kprime, kc_out, soft;
+    int n_split;            // reference ranges per query item (work item = n_items x n_split, see nabo_tc_split)
     unsigned long long* cand_buf;   // [gridDim][NQ*TILE][CAP]
-    int32_t* cand_idx;      // [n_query][kc_out]
-    float* cert_tau;        // [n_query]
+    int32_t* cand_idx;      // [n_query][n_split][kc_out]
+    float* cert_tau;        // [n_split][n_query]
     size_t a_off, b_off, sort_off, bar_off;
 };
 
@@ -231,6 +232,14 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid
     }
 }
 
+// work item w -> (query item, first / last reference tile of its range)
+__device__ __forceinline__ void decode_item(const Params& p, int w, int& qitem, int& seg, int& j0, int& j1) {
+    qitem = w / p.n_split;
+    seg = w - qitem * p.n_split;
+    j0 = (int)((long long)p.n_rtiles * seg / p.n_split);
+    j1 = (int)((long long)p.n_rtiles * (seg + 1) / p.n_split);
+}
+
 template <int KSTEPS>   // K steps of 16 known at compile time (0 = runtime loop)
 __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -257,7 +266,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t t = 0, it = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+            for (int w = blockIdx.x; w < p.n_items * p.n_split; w += gridDim.x, ++it) {
+                int item, seg, j0, j1;
+                decode_item(p, w, item, seg, j0, j1);
                 ptx::mbar_wait(&bars->a_empty, (it & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&bars->a_full, NQ * a_tile_bytes);
                 for (int q = 0; q < NQ; ++q) {
@@ -266,7 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                     for (uint32_t o = 0; o < a_tile_bytes; o += 8192)
                         ptx::bulk_g2s(dst + o, src + o, min(8192u, a_tile_bytes - o), &bars->a_full);
                 }
-                for (int j = 0; j < p.n_rtiles; ++j, ++t) {
+                for (int j = j0; j < j1; ++j, ++t) {
                     const uint32_t s = t % p.stages, use = t / p.stages;
                     ptx::mbar_wait(&bars->b_empty[s], (use & 1) ^ 1);
                     ptx::mbar_arrive_expect_tx(&bars->b_full[s], a_tile_bytes);
@@ -292,9 +303,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
             const uint64_t ad0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.a_off), lbo, sbo);
             const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off), lbo, sbo);
             uint32_t t = 0, it = 0, n = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+            for (int w = blockIdx.x; w < p.n_items * p.n_split; w += gridDim.x, ++it) {
+                int item, seg, j0, j1;
+                decode_item(p, w, item, seg, j0, j1);
                 ptx::mbar_wait(&bars->a_full, it & 1);
-                for (int j = 0; j < p.n_rtiles; ++j, ++t) {
+                for (int j = j0; j < j1; ++j, ++t) {
                     const uint32_t s = t % p.stages, use = t / p.stages;
                     ptx::mbar_wait(&bars->b_full[s], use & 1);
                     const uint64_t bd1 = bd0 + (uint64_t)((s * a_tile_bytes) >> 4);
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                             ptx::mma_commit(&bars->acc_full[buf]);
                             if (q == NQ - 1) {
                                 ptx::mma_commit(&bars->b_empty[s]);
-                                if (j == p.n_rtiles - 1) ptx::mma_commit(&bars->a_empty);
+                                if (j == j1 - 1) ptx::mma_commit(&bars->a_empty);
                             }
                         }
                         __syncwarp();
@@ -343,9 +356,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
             const uint64_t ad0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.a_off) + q * a_tile_bytes, lbo, sbo);
             const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off), lbo, sbo);
             uint32_t t = 0, it = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+            for (int w = blockIdx.x; w < p.n_items * p.n_split; w += gridDim.x, ++it) {
+                int item, seg, j0, j1;
+                decode_item(p, w, item, seg, j0, j1);
                 ptx::mbar_wait(&bars->a_full, it & 1);
-                for (int j = 0; j < p.n_rtiles; ++j, ++t) {
+                for (int j = j0; j < j1; ++j, ++t) {
                     const uint32_t s = t % p.stages, use = t / p.stages;
                     ptx::mbar_wait(&bars->acc_empty[q], (t & 1) ^ 1);
                     ptx::mbar_wait(&bars->b_full[s], use & 1);
@@ -365,7 +380,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                         }
                         ptx::mma_commit(&bars->acc_full[q]);
                         ptx::mma_commit(&bars->b_empty[s]);
-                        if (j == p.n_rtiles - 1) ptx::mma_commit(&bars->a_empty);
+                        if (j == j1 - 1) ptx::mma_commit(&bars->a_empty);
                     }
                     __syncwarp();
                 }
@@ -382,10 +397,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         uint32_t t = 0;
         uint32_t ks[4], kpl[4];
         uint32_t* hist = reinterpret_cast<uint32_t*>(smem + p.sort_off) + (size_t)warp * 256;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int w = blockIdx.x; w < p.n_items * p.n_split; w += gridDim.x) {
+            int item, seg, j0, j1;
+            decode_item(p, w, item, seg, j0, j1);
             float tau = CUDART_INF_F;
             int cnt = 0;
-            for (int j = 0; j < p.n_rtiles; ++j, ++t) {
+            for (int j = j0; j < j1; ++j, ++t) {
 #if NABO_TC_ROTATE
                 const uint32_t job = t * NQ + q, buf = job & 3, acc_par = (job >> 2) & 1;
 #else
@@ -437,9 +454,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int i = u * 32 + lane;
-                        if (i < p.kc_out) p.cand_idx[qg * p.kc_out + i] = i < nc ? (int32_t)kpl[u] : -1;
+                        if (i < p.kc_out)
+                            p.cand_idx[(qg * p.n_split + seg) * p.kc_out + i] = i < nc ? (int32_t)kpl[u] : -1;
                     }
-                    if (lane == 0) p.cert_tau[qg] = n >= p.kprime ? nt : old_tau;
+                    if (lane == 0) p.cert_tau[(long long)seg * p.n_query + qg] = n >= p.kprime ? nt : old_tau;
                 }
             }
         }
@@ -477,6 +495,27 @@ static int tc_grid(int n_items) {
     return n_items < sms ? n_items : sms;
 }
 
+// With fewer query items than SMs the reference range of every item is cut into up to NABO_TC_MAX_SPLIT
+// pieces, each a work item of its own with its own K' candidates and threshold: a 20 000-query call keeps
+// 106 SMs busy instead of 53.  The re-rank sees the union of the candidate lists and the smallest threshold
+// (everything a piece rejected scored >= that piece's threshold >= the minimum), so nothing else changes.
+int nabo_tc_split(int n_query, int n_ref) {
+    const int n_items = (n_query + tc::NQ * tc::TILE - 1) / (tc::NQ * tc::TILE);
+    const int n_rtiles = (n_ref + tc::TILE - 1) / tc::TILE;
+    int s = n_items > 0 ? tc_grid(1 << 30) / n_items : 1;
+    if (s > NABO_TC_MAX_SPLIT) s = NABO_TC_MAX_SPLIT;
+    while (s > 1 && n_rtiles / s < 32) --s;              // keep >= 4096 references per piece
+    return s < 1 ? 1 : s;
+}
+
+__global__ void tau_min_kernel(float* __restrict__ tau, int n_query, int n_split) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_query) return;
+    float t = tau[i];
+    for (int s = 1; s < n_split; ++s) t = fminf(t, tau[(size_t)s * n_query + i]);
+    tau[i] = t;
+}
+
 size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_first) {
     const int kp = tc::kp_for(g);
     const size_t tb = tc::tile_bytes(kp);
@@ -489,8 +528,8 @@ size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_fi
     b += nabo_align_up((size_t)n_query * 8, 256) * 2;                 // q norms, qn2
     b += nabo_align_up((size_t)n_ref * 8, 256);                       // r norms
     b += nabo_align_up((size_t)148 * tc::NQ * tc::TILE * tc::CAP * 8, 256);   // candidate buffers
-    b += nabo_align_up((size_t)n_query * kprime * 4, 256);            // candidate indices
-    b += nabo_align_up((size_t)n_query * 4, 256) * 2;                 // cert tau, fail rows
+    b += nabo_align_up((size_t)n_query * kprime * 4 * NABO_TC_MAX_SPLIT, 256);   // candidate indices (per reference range)
+    b += nabo_align_up((size_t)n_query * 4 * NABO_TC_MAX_SPLIT, 256) + nabo_align_up((size_t)n_query * 4, 256);   // cert tau, fail rows
     b += 4096;
     return b;
 }
@@ -498,7 +537,7 @@ size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_fi
 // Runs norms -> scale -> pack -> candidate kernel.  Outputs (device, inside the arena):
 // cand_idx [n_query][kprime], cert_tau [n_query], qn2 [n_query], scal[4].
 int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
-                       int metric, const uint8_t* mask, int drop_first, NaboArena& ar, int32_t** cand_idx_out,
+                       int metric, const uint8_t* mask, int drop_first, int n_split, NaboArena& ar, int32_t** cand_idx_out,
                        int* kprime_out, float** cert_tau_out, double** qn2_out, double** scal_out, int* launches,
                        NaboStageTimer& tm, cudaStream_t st) {
     const int kp = tc::kp_for(g);
@@ -508,7 +547,8 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     const int n_qtiles = n_items * tc::NQ;
     const int n_rtiles = (n_ref + tc::TILE - 1) / tc::TILE;
     const int kprime = nabo_tc_kprime(k, drop_first);
-    const int grid = tc_grid(n_items);
+    if (n_split < 1 || n_split > NABO_TC_MAX_SPLIT) n_split = 1;
+    const int grid = tc_grid(n_items * n_split);
 
     __half* qa = (__half*)ar.take<char>((size_t)n_qtiles * tb);
     __half* rb = (__half*)ar.take<char>((size_t)n_rtiles * tb);
@@ -516,8 +556,8 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     double* qn2 = ar.take<double>(n_query);
     double* rnorm = ar.take<double>(n_ref);
     unsigned long long* cbuf = ar.take<unsigned long long>((size_t)grid * tc::NQ * tc::TILE * tc::CAP);
-    int32_t* cand = ar.take<int32_t>((size_t)n_query * kprime);
-    float* tau = ar.take<float>(n_query);
+    int32_t* cand = ar.take<int32_t>((size_t)n_query * kprime * n_split);
+    float* tau = ar.take<float>((size_t)n_query * n_split);
     double* scal = ar.take<double>(4);
     unsigned int* maxbits = ar.take<unsigned int>(2);
     if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small for the tensor-core pass");
@@ -534,7 +574,7 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     tc::Params p;
     p.qa = qa; p.rb = rb;
     p.n_query = n_query; p.n_ref = n_ref; p.kp = kp; p.n_items = n_items; p.n_rtiles = n_rtiles;
-    p.stages = pl.stages; p.kprime = kprime; p.kc_out = kprime;
+    p.stages = pl.stages; p.kprime = kprime; p.kc_out = kprime; p.n_split = n_split;
     p.cand_buf = cbuf; p.cand_idx = cand; p.cert_tau = tau;
     p.a_off = pl.a_off; p.b_off = pl.b_off; p.sort_off = pl.sort_off; p.bar_off = pl.bar_off;
     p.soft = tc::CAP - tc::CHUNK - 16 > kprime ? tc::CAP - tc::CHUNK - 16 : kprime;
@@ -549,6 +589,11 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     else NABO_TC_LAUNCH(0);
 #undef NABO_TC_LAUNCH
     NABO_LAUNCH_CHECK("candidates_kernel");
+    if (n_split > 1) {
+        tau_min_kernel<<<(n_query + 255) / 256, 256, 0, st>>>(tau, n_query, n_split);
+        NABO_LAUNCH_CHECK("tau_min_kernel");
+        *launches += 1;
+    }
     tm.end(0);
     *cand_idx_out = cand; *kprime_out = kprime; *cert_tau_out = tau; *qn2_out = qn2; *scal_out = scal;
     *launches += 6;
@@ -578,7 +623,7 @@ extern "C" int nabo_knn_candidates(const double* q, int ldq, const double* r, in
     float* tau = nullptr;
     double *qn2 = nullptr, *scal = nullptr;
     int kprime = 0, launches = 0;
-    int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, ref_mask, drop_first, ar, &cand, &kprime,
+    int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, ref_mask, drop_first, 1, ar, &cand, &kprime,
                                 &tau, &qn2, &scal, &launches, tm, st);
     if (rc) return rc;
     NABO_CUDA(cudaMemcpyAsync(out_cand, cand, sizeof(int32_t) * (size_t)n_query * kprime, cudaMemcpyDeviceToDevice, st));
