@@ -10,16 +10,18 @@
 // pre-tiled in HBM in the UMMA K-major no-swizzle core-matrix layout (pack kernels below),
 // so one tile is one contiguous span and a single cp.async.bulk brings it in.
 //
-// CTA = 512 threads, persistent over work items of NQ=3 query tiles (384 queries):
+// CTA = 512 threads, persistent over work items of NQ=3 query tiles (384 queries) x one range of
+// reference tiles (the whole reference, or a piece of it when there are fewer items than SMs):
 //   warps 0-11  epilogue: warpgroup w owns query tile w; thread = one query row (TMEM lane)
 //   warp 12  TMEM allocator, then TMA producer: A tiles once per item, B (reference) tiles through a ring
-//   warps 13-15  one MMA issuer thread per query tile, each asleep on its own accumulator barrier
+//   warp 13  MMA issuer: the three query tiles rotate over FOUR accumulators, so the MMAs of a warpgroup's
+//            next tile run while it still reads the current one (warps 14-15 idle)
 // The epilogue keeps, per query, a running threshold tau (register) and a private
 // candidate buffer of CAP keys in L2-resident global memory; a tile chunk is first reduced
 // with FMNMX3 and only chunks holding a score < tau take the append path.  When a buffer
-// may overflow the warp sorts it (bitonic, shared-memory staging), keeps the K' best and
-// tightens tau.  Everything rejected or dropped has score >= final tau, which is what the
-// certificate in the re-rank needs.
+// may overflow the warp compacts it (histogram cut in shared memory, select.cuh), keeps at least
+// the K' best and tightens tau.  Everything rejected or dropped has score >= final tau, which is
+// what the certificate in the re-rank needs.
 #include "common.cuh"
 #include "knn_internal.cuh"
 #include "ptx.cuh"
