@@ -107,13 +107,24 @@ class Graph(nx.Graph):
         dup = [n for n in new_nodes if n in existing]
         for n in dup:
             print("WARNING: node %s already present in the graph. Will not add." % n)
+        n_edges = len(edges["u"]) if isinstance(edges, dict) else len(edges[0])
         if materialize is None:
-            materialize = len(edges[0]) <= 5_000_000
+            materialize = n_edges <= 5_000_000
         if materialize:
-            attrs = {"kind": kind, "name": name}
-            self.add_nodes_from((n for n in new_nodes if n not in existing), **attrs)
-            a, b, w = edges
-            self.add_weighted_edges_from(zip(a, b, w))
+            import gc
+            gc_was_on = gc.isenabled()
+            gc.disable()            # millions of small dicts: the cyclic collector would rescan them over and over
+            try:
+                attrs = {"kind": kind, "name": name}
+                self.add_nodes_from((n for n in new_nodes if n not in existing), **attrs)
+                if isinstance(edges, dict):
+                    self._bulk_add_indexed_edges(edges["names"], edges["u"], edges["v"], edges["w"], fresh=not dup)
+                else:
+                    a, b, w = edges
+                    self.add_weighted_edges_from(zip(a, b, w))
+            finally:
+                if gc_was_on:
+                    gc.enable()
         if kind == "reference":
             self.refName = name
             self.refNodes = [n for n in new_nodes if n not in existing]
@@ -145,21 +156,17 @@ class Graph(nx.Graph):
             last = np.ones(len(hi), dtype=bool)
             last[:-1] = (hi[:-1] != hi[1:]) | (lo[:-1] != lo[1:])
             hi, lo, w = hi[last], lo[last], w[last]
-            a = [nodes[i] for i in lo]
-            b = [nodes[i] for i in hi]
-            w = list(w)
+            u, v = lo.astype(np.int64), hi.astype(np.int64)
             if "fix_edges" in g:
                 fw = float(g["fix_weight"][0])
-                self._samples[name].fix_edges = np.asarray(g["fix_edges"][:], dtype=np.int64)
-                for x, y in np.asarray(g["fix_edges"][:]):
-                    a.append(nodes[int(x)])
-                    b.append(nodes[int(y)])
-                    w.append(fw)
-            return nodes, (a, b, w)
+                fx = np.asarray(g["fix_edges"][:], dtype=np.int64)
+                self._samples[name].fix_edges = fx
+                u, v = np.concatenate([u, fx[:, 0]]), np.concatenate([v, fx[:, 1]])
+                w = np.concatenate([w, np.full(len(fx), fw)])
+            return nodes, {"names": nodes, "u": u, "v": v, "w": w}
         ref_names = [c + "_" + ref_suffix for c in ref_cells]
-        a = [nodes[i] for i in rows]
-        b = [ref_names[j] for j in nb]
-        return nodes, (a, b, list(w))
+        # one name space: the sample's own nodes first, then the reference nodes
+        return nodes, {"names": nodes + ref_names, "u": rows.astype(np.int64), "v": nb.astype(np.int64) + len(nodes), "w": w}
 
     def _load_per_node(self, g: Group, name: str, kind: str, ref_cells: List[str]):
         """Reference layout: dataset per node = rows of [neighbour name, str(weight)] (nabo/_mapping.py:265-270)."""
@@ -187,6 +194,31 @@ class Graph(nx.Graph):
             s.weights = wts
             self._samples[name] = s
         return nodes, (a, b, w)
+
+    def _bulk_add_indexed_edges(self, names, u, v, w, fresh: bool) -> None:
+        """``add_weighted_edges_from`` for the edge table of a columnar graph group (u[i], v[i] index ``names``).
+        With ``fresh`` (the sample's nodes were all new, so none of these edges exists yet) the adjacency dicts
+        are filled per node with C-level ``dict.update`` calls - same adjacency order (edge position) and the
+        same shared attribute dict per edge as networkx builds - instead of one interpreter round trip per edge
+        (3 M edges: 3.5 s -> ~1 s).  Otherwise it goes through networkx itself."""
+        names_arr = np.empty(len(names), dtype=object)
+        names_arr[:] = names
+        wl = np.asarray(w, dtype=np.float64).tolist()
+        if not fresh:
+            self.add_weighted_edges_from(zip(names_arr[u].tolist(), names_arr[v].tolist(), wl))
+            return
+        n_e = len(wl)
+        dds = np.empty(n_e, dtype=object)
+        dds[:] = [{"weight": x} for x in wl]
+        node = np.concatenate([u, v])
+        other = np.concatenate([v, u])
+        pos = np.concatenate([2 * np.arange(n_e), 2 * np.arange(n_e) + 1])       # networkx writes adj[u][v], then adj[v][u]
+        order = np.lexsort((pos, node))
+        node, other_names, dd = node[order], names_arr[other[order]], dds[np.concatenate([np.arange(n_e)] * 2)[order]]
+        bounds = np.flatnonzero(np.r_[True, node[1:] != node[:-1], True]) if len(node) else np.zeros(1, dtype=np.int64)
+        adj = self._adj
+        for lo, hi in zip(bounds[:-1].tolist(), bounds[1:].tolist()):
+            adj[names[node[lo]]].update(zip(other_names[lo:hi].tolist(), dd[lo:hi].tolist()))
 
     # ------------------------------------------------------------------ mapping score
     def get_mapping_score(self, target: str, min_weight: float = 0, min_score: float = 0, weighted: bool = True,
