@@ -28,7 +28,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from . import core
-from .store import Group, RowGroup, open_file
+from .store import batched_writes, Group, RowGroup, open_file
 
 __all__ = ["Mapping", "read_matrix"]
 
@@ -319,10 +319,11 @@ class Mapping:
     def make_ref_graph(self, use_stored_distances: bool = False, *, metric: Optional[str] = None,
                        mode: str = "fast"):
         """nabo/_mapping.py:526-541."""
-        if use_stored_distances is False:
-            self.calc_dist(self._refPcaFn, self._refPcaGrp, self._refDistGrp, self._refSortedDistGrp, [],
-                           metric=metric, mode=mode)
-        self.calc_snn(self._refSortedDistGrp, self.refName, self._refGraphGrpName)
+        with batched_writes(self._h5Fn):                   # distances + graph: one rewrite of the mapping file
+            if use_stored_distances is False:
+                self.calc_dist(self._refPcaFn, self._refPcaGrp, self._refDistGrp, self._refSortedDistGrp, [],
+                               metric=metric, mode=mode)
+            self.calc_snn(self._refSortedDistGrp, self.refName, self._refGraphGrpName)
 
     def map_target(self, target_name: str, target_pca_fn: str, target_pca_grp_name: str,
                    ignore_ref_cells: List[str] = None, use_stored_distances: bool = False,
@@ -352,13 +353,14 @@ class Mapping:
             if overwrite is False and target_name in self._nameStash:
                 raise ValueError("ERROR: Data with this target name exists. Please set overwrite=True if you "
                                  "want to map this target again.")
-        self._stash_target_name(target_name)
-        self._check_h5(target_pca_fn, target_pca_grp_name)
-        uid = self._nameStash[target_name]
-        self.calc_dist(target_pca_fn, target_pca_grp_name, uid + "_dist", uid + "_sortedDist", ignore_ref_cells,
-                       metric=metric, mode=mode)
-        self.calc_snn(uid + "_sortedDist", target_name, uid + "_graph")
-        return None
+        with batched_writes(self._h5Fn):                   # name stash + distances + graph: one rewrite
+            self._stash_target_name(target_name)
+            self._check_h5(target_pca_fn, target_pca_grp_name)
+            uid = self._nameStash[target_name]
+            self.calc_dist(target_pca_fn, target_pca_grp_name, uid + "_dist", uid + "_sortedDist", ignore_ref_cells,
+                           metric=metric, mode=mode)
+            self.calc_snn(uid + "_sortedDist", target_name, uid + "_graph")
+            return None
 
 
 def _rows_in_order(grp, order: Optional[List[str]]):

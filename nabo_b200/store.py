@@ -282,6 +282,42 @@ def _stat_key(fn: str):
     return (st.st_mtime_ns, st.st_size)
 
 
+# Files whose writes are being batched (see `batched_writes`): abs path -> content tree waiting to be written
+_DEFERRED: Dict[str, Optional[dict]] = {}
+
+
+class batched_writes:
+    """``with batched_writes(fn): ...`` - every flush / close of ``fn`` inside the block only records the
+    content; the container is written once when the block ends.  The facade wraps its multi-step calls
+    (``Mapping.map_target`` = stash name + distances + graph) in it: three rewrites of a growing file become one.
+    Re-opening the file inside the block sees the pending content."""
+
+    def __init__(self, fn: str):
+        self.key = os.path.abspath(str(fn))
+        self.fn = str(fn)
+        self.outer = False
+
+    def __enter__(self):
+        self.outer = self.key in _DEFERRED
+        if not self.outer:
+            _DEFERRED[self.key] = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.outer:
+            return False
+        pending = _DEFERRED.pop(self.key, None)
+        if pending is not None:
+            f = File.__new__(File)
+            Group.__init__(f, "/", None)
+            f._root, f.filename, f.mode, f._dirty, f._open = f, self.fn, "a", True, True
+            f._c = pending
+            _reroot(f, f)
+            f._persist()
+            f._open = False
+        return False
+
+
 class File(Group):
     """``File(fn, mode)`` with h5py's mode letters: r, r+, a, w, w-/x."""
 
@@ -293,7 +329,8 @@ class File(Group):
         self._dirty = False
         self._open = True
         exists = (self.filename in MEMORY_FILES) if _MEMORY_ONLY else \
-            (os.path.exists(self.filename) and os.path.getsize(self.filename) > 0)
+            ((os.path.exists(self.filename) and os.path.getsize(self.filename) > 0) or
+             _DEFERRED.get(os.path.abspath(self.filename)) is not None)
         if mode in ("r", "r+") and not exists:
             raise OSError("Unable to open file (unable to open file: name = %r)" % self.filename)
         if mode in ("w-", "x") and exists:
@@ -307,6 +344,12 @@ class File(Group):
 
     # -- persistence
     def _load(self):
+        pending = _DEFERRED.get(os.path.abspath(self.filename))
+        if pending is not None:                     # inside batched_writes: the newest content is not on disk yet
+            self._c = pending
+            _reroot(self, self)
+            self._dirty = False
+            return
         if _MEMORY_ONLY:
             self._c = MEMORY_FILES[self.filename]._c
             _reroot(self, self)
@@ -334,6 +377,13 @@ class File(Group):
         self._dirty = False
 
     def _persist(self):
+        key = os.path.abspath(self.filename)
+        if key in _DEFERRED and not _MEMORY_ONLY:
+            _DEFERRED[key] = self._c                # written once, when the batched_writes block ends
+            if not os.path.exists(self.filename):
+                open(self.filename, "ab").close()
+            self._dirty = False
+            return
         if _MEMORY_ONLY:
             holder = MEMORY_FILES.setdefault(self.filename, Group("/"))
             holder._c = self._c

@@ -155,3 +155,42 @@ def test_reopen_uses_cached_content_and_notices_foreign_writes(tmp_path):
     os.utime(fn, ns=(1, 1))
     with store.File(fn, "r") as h:
         assert "only" in h and "data" not in h
+
+
+def test_batched_writes_defer_and_replay(tmp_path):
+    """Inside batched_writes every close only records the content (re-opens see it), the file is written once
+    at the end; nested blocks join the outer one; a block without writes leaves the file alone."""
+    import os
+    from nabo_b200 import store
+    fn = str(tmp_path / "m.h5")
+    with store.File(fn, "w") as h:
+        h.create_dataset("a", data=np.array([1]))
+    before = os.stat(fn).st_mtime_ns
+    with store.batched_writes(fn):
+        with store.File(fn, "a") as h:
+            h.create_dataset("b", data=np.array([2]))
+        with store.batched_writes(fn):                        # nested: same batch
+            with store.File(fn, "a") as h:
+                assert h["b"][0] == 2                         # pending content is visible
+                h.create_row_group("rows", ["x", "y"], np.eye(2))
+        assert os.stat(fn).st_mtime_ns == before              # nothing written yet
+        with store.File(fn, "r") as h:
+            assert "rows" in h and h["rows"]["y"][:].tolist() == [0.0, 1.0]
+    assert os.stat(fn).st_mtime_ns != before
+    store._CONTENT_CACHE.clear()                              # force a real parse of what was written
+    with store.File(fn, "r") as h:
+        assert h["a"][0] == 1 and h["b"][0] == 2 and h["rows"]["x"][:].tolist() == [1.0, 0.0]
+    new = str(tmp_path / "n.h5")
+    with store.batched_writes(new):                           # a file born inside a batch
+        with store.File(new, "w") as h:
+            h.create_dataset("z", data=np.array([9]))
+        with store.File(new, "a") as h:
+            assert h["z"][0] == 9
+    store._CONTENT_CACHE.clear()
+    with store.File(new, "r") as h:
+        assert h["z"][0] == 9
+    stamp = os.stat(fn).st_mtime_ns
+    with store.batched_writes(fn):
+        with store.File(fn, "r") as h:
+            assert "a" in h
+    assert os.stat(fn).st_mtime_ns == stamp
