@@ -11,7 +11,9 @@ same exceptions, same mapping-file group names (``name_stash``, ``ref_cells``,
   ``<uid>_sortedDist/<cell>[j]``;
 * ``<uid>_graph`` is columnar (``nodes``, ``knn``, ``snn``, ``k``, optional repair edges)
   instead of one string-encoded dataset per node (:252-273); ``Graph.load_from_h5``
-  reads both layouts;
+  reads both layouts, and ``Mapping.graph_layout = 'reference'`` (or ``calc_snn(...,
+  graph_layout='reference')``) writes the reference's own per-node layout, which the unmodified
+  ``nabo.Graph`` reads (tests/golden/verify_reference_reader.py);
 * ``chunk_size`` is accepted and validated but has no effect (results never depended on
   it, :106-128);
 * new keyword-only extensions with reference-preserving defaults: ``metric`` (None ->
@@ -83,6 +85,7 @@ class Mapping:
         self._refGraphGrpName = uid + "_graph"
         self._useComps = None
         self._k = None
+        self.graph_layout = "columnar"      # 'reference' = per-node datasets as nabo's _dump_graph writes them
         self._distFactor = None
         self._chunkSize = None
         self._refMatCache = None
@@ -227,9 +230,14 @@ class Mapping:
 
     # ------------------------------------------------------------------ SNN graph
     def calc_snn(self, target_sorted_dist_grp: str, target_name: str, graph_grp: str,
-                 fix_graph_attempts: int = 5, fix_weight: float = None) -> None:
+                 fix_graph_attempts: int = 5, fix_weight: float = None, *, graph_layout: Optional[str] = None) -> None:
         """nabo/_mapping.py:446-493 + _calc_snn :151-200 (+ _fix_disconnected_graph :203-249 for the
-        reference graph, re-expressed as masked nearest-neighbour queries)."""
+        reference graph, re-expressed as masked nearest-neighbour queries).  ``graph_layout='reference'``
+        writes the group the way ``_dump_graph`` does (:252-273: one dataset per node, rows of
+        [neighbour name, str(weight)]) so that the reference's own ``Graph.load_from_h5`` can read it."""
+        layout = graph_layout or self.graph_layout
+        if layout not in ("columnar", "reference"):
+            raise ValueError("ERROR: graph_layout must be 'columnar' or 'reference'")
         if self._k is None:
             raise ValueError("ERROR: Set parameters first")
         k = self._k
@@ -258,6 +266,12 @@ class Mapping:
         if graph_grp in out:
             del out[graph_grp]
         g = out.create_group(graph_grp)
+        if layout == "reference":
+            _write_reference_layout(g, tnames, target_name, rnames, self.refName, tk, np.asarray(cnt), k,
+                                    fix_edges, fw, undirected=target_name == self.refName)
+            out.flush()
+            out.close()
+            return None
         g.create_dataset("nodes", data=np.array([(n + "_" + target_name).encode("ascii") for n in tnames]))
         g.create_dataset("knn", data=tk)
         g.create_dataset("snn", data=np.asarray(cnt, dtype=np.uint8))
@@ -361,6 +375,44 @@ class Mapping:
                            metric=metric, mode=mode)
             self.calc_snn(uid + "_sortedDist", target_name, uid + "_graph")
             return None
+
+
+def _write_reference_layout(g, tnames, target_name, rnames, ref_name, knn, cnt, k, fix_edges, fix_w, undirected):
+    """The reference's ``_dump_graph`` layout (nabo/_mapping.py:252-273): one dataset per node holding its
+    incident edges as rows [neighbour node name, weight]; NumPy coerces a (bytes, float) row to byte strings, so
+    the weight is stored as its decimal string, exactly like upstream.  For the reference graph (undirected,
+    targets = reference cells) a node lists every incident edge, with the weight of the LAST add_edge for that
+    pair (:196-198) and the repair edges."""
+    lut = core.snn_weight_lut(k)
+    rows, cols = np.nonzero(cnt > 0)
+    nb = knn[rows, cols].astype(np.int64)
+    w = lut[cnt[rows, cols]]
+    ref_nodes = [c + "_" + ref_name for c in rnames]
+    own_nodes = [c + "_" + target_name for c in tnames]
+    if undirected:
+        hi, lo = np.maximum(rows, nb), np.minimum(rows, nb)
+        order = np.lexsort((rows >= nb, lo, hi))            # per pair: the edge seen from max(a, b) is added last
+        hi, lo, w = hi[order], lo[order], w[order]
+        last = np.ones(len(hi), dtype=bool)
+        last[:-1] = (hi[:-1] != hi[1:]) | (lo[:-1] != lo[1:])
+        hi, lo, w = hi[last], lo[last], w[last]
+        if len(fix_edges):
+            lo = np.concatenate([lo, fix_edges[:, 0]])
+            hi = np.concatenate([hi, fix_edges[:, 1]])
+            w = np.concatenate([w, np.full(len(fix_edges), fix_w)])
+        src = np.concatenate([lo, hi])
+        dst = np.concatenate([hi, lo])
+        w = np.concatenate([w, w])
+        names_dst = own_nodes
+    else:
+        src, dst, names_dst = rows, nb, ref_nodes
+    order = np.argsort(src, kind="stable")
+    src, dst, w = src[order], dst[order], w[order]
+    bounds = np.searchsorted(src, np.arange(len(own_nodes) + 1))
+    for i, node in enumerate(own_nodes):
+        lo_, hi_ = bounds[i], bounds[i + 1]
+        temp = [(names_dst[int(j)].encode("ascii"), float(x)) for j, x in zip(dst[lo_:hi_], w[lo_:hi_])]
+        g.create_dataset(node, data=np.array(temp) if temp else np.zeros((0, 2), dtype="S32"))
 
 
 def _rows_in_order(grp, order: Optional[List[str]]):

@@ -282,3 +282,48 @@ def test_mapping_edge_semantics(tmp_path, golden):
         assert (td[t, :n_live] == uc).all()
     gr = g["ref_sorted_full"][:, :k].astype(np.int64)
     assert O.tie_classes_equal(rk, rd, gr, np.take_along_axis(g["ref_dist_full"], gr, 1), head_truncated=True)
+
+
+def test_reference_graph_layout_roundtrip(tmp_path, golden):
+    """graph_layout='reference': the mapping file carries nabo's own per-node graph groups (rows of
+    [neighbour name, str(weight)], _dump_graph) - the layout the reference's Graph reads - and loading them
+    gives the reference's edges, scores and specificity."""
+    from nabo_b200 import Mapping, Graph, store, synth
+    g = golden("mapping_small")
+    uc, k, f = int(g["use_comps"]), int(g["k"]), float(g["f"])
+    ref, tgt = g["ref"], g["tgt"]
+    rn, tn = synth.cell_names(len(ref), "R"), synth.cell_names(len(tgt), "T")
+    ref_fn, tgt_fn, map_fn = (str(tmp_path / x) for x in ("ref.h5", "tgt.h5", "map.h5"))
+    _write_pca(ref_fn, rn, ref)
+    _write_pca(tgt_fn, tn, tgt)
+    random.seed(5)
+    m = Mapping(map_fn, "REF", ref_fn, "data", overwrite=True)
+    m.graph_layout = "reference"
+    m.set_parameters(uc, k, f, 64)
+    m.make_ref_graph()
+    m.map_target("TGT", tgt_fn, "data")
+    h5 = store.File(map_fn, "r")
+    tuid = [i[1].decode() for i in h5["name_stash/target_names"] if i[0] == b"TGT"][0]
+    node = h5[tuid + "_graph"][tn[0] + "_TGT"]
+    assert str(node.dtype) == str(g["graph_dtype"]) and node.shape[1] == 2          # byte strings, as upstream
+    assert "knn" not in h5[tuid + "_graph"]
+    h5.close()
+    gph = Graph()
+    gph.load_from_h5(map_fn, "REF", "reference")
+    gph.load_from_h5(map_fn, "TGT", "target")
+    exp = {(tn[int(t)] + "_TGT", rn[int(r)] + "_REF"): float(w)
+           for t, r, w in zip(g["tgt_edge_t"], g["tgt_edge_r"], g["tgt_edge_w"])}
+    got = {(a, b) if a.endswith("_TGT") else (b, a): d["weight"]
+           for a, b, d in gph.edges(data=True) if a.endswith("_TGT") or b.endswith("_TGT")}
+    assert got == exp
+    exp_ref = {frozenset((rn[int(a)], rn[int(b)])): float(w)
+               for a, b, w in zip(g["ref_edge_a"], g["ref_edge_b"], g["ref_edge_w"])}
+    got_ref = {frozenset((a[:-4], b[:-4])): d["weight"] for a, b, d in gph.refG.edges(data=True)}
+    assert got_ref == exp_ref
+    sc = gph.get_mapping_score("TGT")
+    np.testing.assert_allclose(np.array([sc[c + "_REF"] for c in rn]), g["score_default"], rtol=1e-12, atol=0)
+    sp = gph.get_mapping_specificity("TGT", fill_na=False)
+    got_sp = np.array([sp[c + "_TGT"] for c in tn])
+    assert np.array_equal(got_sp, g["specificity_raw"], equal_nan=True)
+    with pytest.raises(ValueError, match="graph_layout"):
+        m.calc_snn("x", "TGT", "y", graph_layout="hdf4")
