@@ -168,6 +168,13 @@ int nabo_sparse_row_stats(const long long* indptr, const int32_t* idx, const flo
                           int want_moments, float* out_sum, float* out_mean, float* out_nzmean,
                           float* out_var, int32_t* out_npos, void* stream);
 
+/* Connected components of an undirected graph (edge list int32): out_labels[i] = smallest node id of
+ * i's component.  Device form of the nx.connected_components call inside the reference-graph repair
+ * (_fix_disconnected_graph, nabo/_mapping.py:203-249).  workspace >= n_nodes * 4 + 512 bytes.
+ * Synchronises the stream (one flag read per sweep over the edges). */
+int nabo_connected_components(const int32_t* edge_a, const int32_t* edge_b, long long n_edges, int n_nodes,
+                              int32_t* out_labels, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- (6) scaling + PCA projection: replaces get_scaled_values + transform_pca ---
  * nabo/_dataset.py:905-913 and :1028 (sklearn IncrementalPCA.transform):
  *   a = counts as float32; z = ((a * sf_i) [float32] - mu) / sigma   [float64]

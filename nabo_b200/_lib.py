@@ -47,6 +47,7 @@ SIGNATURES: Dict[str, tuple] = {
     "nabo_classify_targets": (_i, [_p, _p, _p, _i, _i, _p, _i, _d, _i, _d, _p, _p]),
     "nabo_specificity_workspace_bytes": (_z, [_i, _i]),
     "nabo_mapping_specificity": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _z, _p]),
+    "nabo_connected_components": (_i, [_p, _p, C.c_longlong, _i, _p, _p, _z, _p]),
     "nabo_sparse_row_stats": (_i, [_p, _p, _p, _i, _i, _p, _p, C.c_longlong, _i, _p, _p, _p, _p, _p, _p]),
     "nabo_scale_dense": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p, _i, _p]),
     "nabo_project_dense": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _i, _p]),

@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import METRICS, MODE_EXACT, MODE_FAST, check, lib, require_device
 
 __all__ = ["euclidean_dist", "mod_canberra_dist", "cosine_dist", "knn", "knn_candidates", "rerank_exact", "merge_topk",
-           "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets", "mapping_specificity", "sparse_row_stats",
+           "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets", "mapping_specificity", "sparse_row_stats", "connected_components",
            "project", "project_csr", "scale_counts", "map_cells", "map_cells_host", "resolve_metric"]
 
 
@@ -362,6 +362,22 @@ def mapping_specificity(indptr, indices, tgt_knn, counts):
                        torch.full((n,), float("nan"), dtype=torch.float64, device=td.device))
     connected = opairs.to(torch.int64) >= want
     return _out(mean, host), _out(connected, host)
+
+
+def connected_components(edge_a, edge_b, n_nodes: int):
+    """Component label (= smallest node id of the component) of every node of the undirected graph given by
+    the edge list; the ``nx.connected_components`` of the reference-graph repair (nabo/_mapping.py:203-249)."""
+    require_device()
+    host = _is_host(edge_a, edge_b)
+    ea, eb = _dev(edge_a, torch.int32), _dev(edge_b, torch.int32)
+    if ea.numel() != eb.numel():
+        raise ValueError("ERROR: edge_a and edge_b must have the same length")
+    dev = ea.device
+    lab = torch.empty(int(n_nodes), dtype=torch.int32, device=dev)
+    ws = torch.empty(int(n_nodes) * 4 + 1024, dtype=torch.uint8, device=dev)
+    check(lib().nabo_connected_components(_ptr(ea), _ptr(eb), ea.numel(), int(n_nodes), _ptr(lab), _ptr(ws), ws.numel(),
+                                          C.c_void_p(_stream())), "connected_components")
+    return _out(lab, host)
 
 
 def sparse_row_stats(indptr, idx, val, pos_of_col, n_dense: int, scale=None, moments: bool = True):

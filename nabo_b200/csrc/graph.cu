@@ -409,3 +409,73 @@ extern "C" int nabo_merge_topk(const int32_t* idx, const double* dist, int n_sha
     NABO_LAUNCH_CHECK("merge_kernel");
     return 0;
 }
+
+// ------------------------------------------------------------------ connected components
+// Labels of the connected components of an undirected graph given as an edge list: union-find with
+// atomicMin hooking (the root with the larger id is hooked under the smaller one) and path halving, swept
+// over the edges until a sweep changes nothing; label[i] = smallest node id of i's component, so the
+// result does not depend on scheduling.  Used by the reference-graph repair (_fix_disconnected_graph,
+// nabo/_mapping.py:203-249, works on nx.connected_components).
+__device__ __forceinline__ int cc_find(int* parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        const int gp = parent[p];
+        if (gp != p) parent[x] = gp;          // path halving (benign race: every written value is an ancestor)
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
+__global__ void cc_init_kernel(int* parent, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) parent[i] = i;
+}
+
+__global__ void cc_hook_kernel(const int32_t* __restrict__ ea, const int32_t* __restrict__ eb, long long n_edges,
+                               int n_nodes, int* parent, int* changed) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int a = ea[e], b = eb[e];
+    if (a < 0 || b < 0 || a >= n_nodes || b >= n_nodes || a == b) return;
+    int ra = cc_find(parent, a), rb = cc_find(parent, b);
+    while (ra != rb) {
+        const int hi = ra > rb ? ra : rb, lo = ra > rb ? rb : ra;
+        const int old = atomicMin(&parent[hi], lo);
+        if (old == hi) { *changed = 1; break; }       // hooked a root
+        ra = cc_find(parent, old);                     // hi was no longer a root: retry from its new parent
+        rb = lo;
+        *changed = 1;
+    }
+}
+
+__global__ void cc_flatten_kernel(int* parent, int n, int32_t* labels) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) labels[i] = cc_find(parent, i);
+}
+
+extern "C" int nabo_connected_components(const int32_t* edge_a, const int32_t* edge_b, long long n_edges, int n_nodes,
+                                         int32_t* out_labels, void* workspace, size_t workspace_bytes, void* stream) {
+    NABO_ARG(n_nodes >= 1 && n_edges >= 0, "connected_components: bad sizes");
+    NABO_ARG(out_labels && (n_edges == 0 || (edge_a && edge_b)), "connected_components: null pointer");
+    if (workspace == nullptr || workspace_bytes < (size_t)n_nodes * sizeof(int) + 256)
+        return nabo_set_error(NABO_EWORKSPACE, "connected_components: workspace too small (need %zu bytes)",
+                              (size_t)n_nodes * sizeof(int) + 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    int* parent = (int*)workspace;
+    int* changed = (int*)((char*)workspace + nabo_align_up((size_t)n_nodes * sizeof(int), 256));
+    cc_init_kernel<<<(n_nodes + 255) / 256, 256, 0, st>>>(parent, n_nodes);
+    NABO_LAUNCH_CHECK("cc_init_kernel");
+    for (int sweep = 0; sweep < 64 && n_edges > 0; ++sweep) {
+        int h = 0;
+        NABO_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), st));
+        cc_hook_kernel<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(edge_a, edge_b, n_edges, n_nodes, parent, changed);
+        NABO_LAUNCH_CHECK("cc_hook_kernel");
+        NABO_CUDA(cudaMemcpyAsync(&h, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+        NABO_CUDA(cudaStreamSynchronize(st));
+        if (!h) break;
+    }
+    cc_flatten_kernel<<<(n_nodes + 255) / 256, 256, 0, st>>>(parent, n_nodes, out_labels);
+    NABO_LAUNCH_CHECK("cc_flatten_kernel");
+    return 0;
+}

@@ -288,16 +288,20 @@ class Mapping:
         component gets one edge of weight `fix_weight` from the member whose nearest cell inside any
         strictly larger component is closest.  The "walk the full sorted row to the first candidate"
         of the reference is a k=1 query with every non-candidate masked."""
-        import scipy.sparse as sp
-        from scipy.sparse.csgraph import connected_components
         m = knn.shape[0]
         rows = np.repeat(np.arange(m), knn.shape[1])
         sel = (cnt.ravel() > 0) & (knn.ravel() >= 0)
         a, b = rows[sel], knn.ravel()[sel].astype(np.int64)
         fixes: List[Tuple[int, int]] = []
         fw = fix_weight
-        ncomp, lab = connected_components(sp.coo_matrix((np.ones(len(a), np.int8), (a, b)), shape=(m, m)),
-                                          directed=False)
+
+        def components(ea, eb):
+            # union-find on the GPU (nabo_connected_components); labels renumbered 0..ncomp-1
+            lab_min = core.connected_components(ea.astype(np.int32), eb.astype(np.int32), m)
+            uniq, lab = np.unique(lab_min, return_inverse=True)
+            return len(uniq), lab
+
+        ncomp, lab = components(a, b)
         if ncomp > 1:
             if fw is None:
                 fw = core.fix_weight(self._k)
@@ -323,8 +327,7 @@ class Mapping:
             fixes.extend(new)
             ea = np.concatenate([a, np.array([f[0] for f in fixes], dtype=np.int64)])
             eb = np.concatenate([b, np.array([f[1] for f in fixes], dtype=np.int64)])
-            ncomp, lab = connected_components(sp.coo_matrix((np.ones(len(ea), np.int8), (ea, eb)), shape=(m, m)),
-                                              directed=False)
+            ncomp, lab = components(ea, eb)
         if ncomp > 1:
             print("WARNING: Output graph is disconnected.")
         return np.array(fixes, dtype=np.int64).reshape(-1, 2), fw

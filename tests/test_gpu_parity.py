@@ -341,3 +341,30 @@ def test_mapping_specificity_matches_oracle(core, m, n, k, deg, comps):
     ok = ~np.isnan(exp)
     assert np.array_equal(mean[sel][ok], exp[ok])
     assert np.isnan(mean[0]) and np.isnan(mean[1])
+
+
+@pytest.mark.parametrize("n,deg,seed", [(1, 0, 0), (50, 0, 1), (1000, 1, 2), (5000, 2, 3), (100000, 3, 4), (3000, 40, 5)])
+def test_connected_components_match_scipy(core, n, deg, seed):
+    """GPU union-find labels (= smallest node id of the component) against scipy's connected components on
+    random sparse graphs: isolated nodes, chains, dense blobs, self loops, duplicate and out-of-range edges."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+    rng = np.random.default_rng(seed)
+    e = n * deg // 2
+    a = rng.integers(0, n, size=e).astype(np.int32)
+    b = rng.integers(0, n, size=e).astype(np.int32)
+    if n >= 1000:                                              # a long chain: worst case for label propagation
+        chain = np.arange(0, n // 4 - 1, dtype=np.int32)
+        a, b = np.concatenate([a, chain]), np.concatenate([b, chain + 1])
+    if e:
+        a[:3], b[:3] = a[3:6], a[3:6]                          # self loops
+    lab = core.connected_components(a, b, n)
+    keep = a != b
+    ncomp, ref = connected_components(sp.coo_matrix((np.ones(keep.sum(), np.int8), (a[keep], b[keep])), shape=(n, n)),
+                                      directed=False)
+    assert len(np.unique(lab)) == ncomp
+    # same partition, and every label is the smallest member of its class
+    first = {}
+    for i, (x, y) in enumerate(zip(lab, ref)):
+        assert first.setdefault(y, x) == x
+    assert all(lab[x] == x for x in np.unique(lab)) and (lab <= np.arange(n)).all()
