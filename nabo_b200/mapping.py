@@ -306,7 +306,7 @@ class Mapping:
             if fw is None:
                 fw = core.fix_weight(self._k)
             print("INFO: Reference graph is disconnected. Trying to fix..")
-        ref = self._ref_matrix()
+        ref = None
         for _ in range(attempts):
             if ncomp <= 1:
                 if fixes:
@@ -319,7 +319,12 @@ class Mapping:
                 if not cand.any():
                     continue
                 members = np.nonzero(sizes[lab] == s)[0]
-                idx, dst = core.knn(ref[members], ref, 1, "euclidean", ref_mask=~cand, mode="exact")
+                if ref is None:                             # the reference goes to the device once, not per size class
+                    import torch
+                    ref = torch.from_numpy(np.ascontiguousarray(self._ref_matrix())).cuda()
+                idx, dst = core.knn(ref[torch.from_numpy(members).cuda()], ref, 1, "euclidean",
+                                    ref_mask=torch.from_numpy(~cand).cuda(), mode="fast")
+                idx, dst = idx.cpu().numpy(), dst.cpu().numpy()
                 for comp in np.unique(lab[members]):
                     loc = np.nonzero(lab[members] == comp)[0]
                     best = loc[np.argsort(dst[loc, 0], kind="stable")[0]]
