@@ -1,20 +1,23 @@
 // Mapping specificity (nabo/_graph.py:794-824): for every target cell, the mean of the unweighted
 // shortest-path lengths, in the reference graph, between all pairs of reference cells it maps to.
 // The reference runs one networkx BFS per pair (k(k-1)/2 per target); here ONE bit-parallel multi-source
-// BFS per target finds all pair distances at once:
+// search per target finds all pair distances at once:
 //
-//   * source i of the target owns bit i of a 64-bit mask; cur[v] = sources that have reached node v;
+//   * source i of the target owns bit i of a 64-bit mask; cur[v] = sources whose ball contains node v;
 //   * level L: every frontier node u pushes the bits that reached it at level L-1 (delta[u]) to its
 //     neighbours: acc[v] |= delta[u] & ~cur[v]; a node whose acc was zero joins the next frontier;
-//   * commit: delta[v] = acc[v] & ~cur[v], cur[v] |= delta[v]; when v is itself one of the target's mapped
-//     cells (position j), every newly arrived bit i != j is the pair distance d(i, j) = L;
-//   * stop when all k(k-1) ordered pairs are found (or the frontier dies: no path, reported to the host,
-//     where the reference would raise NetworkXNoPath).
+//   * commit: delta[v] = acc[v] & ~cur[v].  All balls grow in lock step, so the first time bit i arrives
+//     at a node that already holds bit j the pair is 2L - 1 apart, and two bits arriving together are 2L
+//     apart (pass A before pass B, so the shorter meeting always wins): every pair is settled after
+//     ceil(d / 2) levels - the balls stay small - instead of the d levels a one-sided search needs;
+//   * a source that has met every partner stops propagating; the search ends when all k(k-1)/2 pairs
+//     are settled (or the frontier dies: no path, reported to the host, where the reference would raise
+//     NetworkXNoPath).
 //
-// One CTA per target at a time, persistent over the targets; per-CTA scratch (cur, acc, frontier lists,
-// position bytes) lives in the caller's workspace and is cleaned by walking the list of touched nodes, so
-// the arrays are zero again when the next target starts.  Integer outputs (sum of distances, pairs found):
-// exact and independent of scheduling.
+// One CTA per target at a time, persistent over the targets; per-CTA scratch (cur, acc, frontier lists)
+// lives in the caller's workspace and is cleaned by walking the list of touched nodes, so the arrays are
+// zero again when the next target starts.  Integer outputs (sum of distances, pairs found): exact and
+// independent of scheduling.
 #include "common.cuh"
 
 namespace spec {
@@ -45,6 +48,9 @@ specificity_kernel(const long long* __restrict__ indptr, const int32_t* __restri
     __shared__ int s_nt, s_nf[2], s_ntouched;
     __shared__ unsigned long long s_sum;
     __shared__ int s_pairs;
+    __shared__ unsigned long long s_found[MAXK];   // s_found[lo] bit hi: pair {lo, hi} has its distance (lo < hi)
+    __shared__ int s_nfound[MAXK];                 // partners found per source
+    __shared__ unsigned long long s_active;        // sources still missing a partner: only their bits keep travelling
 
     Scratch sc;
     {
@@ -60,6 +66,18 @@ specificity_kernel(const long long* __restrict__ indptr, const int32_t* __restri
         sc.tpos = b;
     }
 
+    // pair {i, j} met with total path length dist: count it once
+    auto record = [&](int i, int j, int dist) {
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        const unsigned long long bit = 1ull << hi;
+        if (!(atomicOr(&s_found[lo], bit) & bit)) {
+            atomicAdd(&s_sum, (unsigned long long)dist);
+            atomicAdd(&s_pairs, 1);
+            atomicAdd(&s_nfound[lo], 1);
+            atomicAdd(&s_nfound[hi], 1);
+        }
+    };
+
     for (int t = blockIdx.x; t < n_query; t += gridDim.x) {
         // ---- the target's mapped reference cells = its edges (snn count > 0), nabo/_mapping.py:195-198
         if (threadIdx.x == 0) {
@@ -74,7 +92,9 @@ specificity_kernel(const long long* __restrict__ indptr, const int32_t* __restri
             s_nf[0] = nt;
             s_nf[1] = 0;
             s_ntouched = nt;
+            s_active = nt >= 64 ? ~0ull : ((1ull << nt) - 1ull);
         }
+        if (threadIdx.x < MAXK) { s_found[threadIdx.x] = 0ull; s_nfound[threadIdx.x] = 0; }
         __syncthreads();
         const int nt = s_nt;
         if (nt < 2) {
@@ -85,22 +105,26 @@ specificity_kernel(const long long* __restrict__ indptr, const int32_t* __restri
         if (threadIdx.x < nt) {
             const int v = s_src[threadIdx.x];
             sc.cur[v] = 1ull << threadIdx.x;
-            sc.tpos[v] = (uint8_t)(threadIdx.x + 1);
             sc.fr[0][threadIdx.x] = v;
             sc.dl[0][threadIdx.x] = 1ull << threadIdx.x;
             sc.touched[threadIdx.x] = v;
         }
         __syncthreads();
 
-        const int want = nt * (nt - 1);
+        // All sources grow their balls in lock step.  When ball i (radius L) first meets ball j at a node, the
+        // pair's distance is 2L - 1 if j was there since the level before, 2L if both arrive now: every pair is
+        // settled after ceil(d / 2) levels, long before a one-sided search from i would reach j.
+        const int want = nt * (nt - 1) / 2;
         int cb = 0;
         for (int level = 1;; ++level) {
             const int nf = s_nf[cb];
+            const unsigned long long active = s_active;
             // ---- expand: one warp per frontier node, lanes over its adjacency
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             for (int f = warp; f < nf; f += NT / 32) {
                 const int u = sc.fr[cb][f];
-                const unsigned long long du = sc.dl[cb][f];
+                const unsigned long long du = sc.dl[cb][f] & active;      // a source that has found every partner stops here
+                if (du == 0ull) continue;
                 const long long e0 = indptr[u], e1 = indptr[u + 1];
                 for (long long e = e0 + lane; e < e1; e += 32) {
                     const int v = indices[e];
@@ -115,7 +139,7 @@ specificity_kernel(const long long* __restrict__ indptr, const int32_t* __restri
                 }
             }
             __syncthreads();
-            // ---- commit the new frontier
+            // ---- commit pass A: new bits meet the bits that were already there (distance 2L - 1)
             const int nn = s_nf[cb ^ 1];
             for (int f = threadIdx.x; f < nn; f += NT) {
                 const int v = sc.fr[cb ^ 1][f];
@@ -125,16 +149,41 @@ specificity_kernel(const long long* __restrict__ indptr, const int32_t* __restri
                 sc.cur[v] = c | d;
                 sc.dl[cb ^ 1][f] = d;
                 if (c == 0ull) sc.touched[atomicAdd(&s_ntouched, 1)] = v;      // first visit of v
-                const int tp = sc.tpos[v];
-                if (tp) {
-                    const int np = __popcll(d & ~(1ull << (tp - 1)));
-                    if (np) {
-                        atomicAdd(&s_sum, (unsigned long long)np * (unsigned long long)level);
-                        atomicAdd(&s_pairs, np);
+                if (c) {
+                    unsigned long long di = d;
+                    while (di) {
+                        const int i = __ffsll((long long)di) - 1;
+                        di &= di - 1;
+                        unsigned long long cj = c;
+                        while (cj) {
+                            const int j = __ffsll((long long)cj) - 1;
+                            cj &= cj - 1;
+                            record(i, j, 2 * level - 1);
+                        }
                     }
                 }
             }
             __syncthreads();
+            // ---- commit pass B: bits that arrive together (distance 2L), after every 2L - 1 meeting is known
+            if (s_pairs < want) {
+                for (int f = threadIdx.x; f < nn; f += NT) {
+                    unsigned long long di = sc.dl[cb ^ 1][f];
+                    if (di & (di - 1)) {                                       // at least two new bits
+                        while (di) {
+                            const int i = __ffsll((long long)di) - 1;
+                            di &= di - 1;
+                            unsigned long long dj = di;
+                            while (dj) {
+                                const int j = __ffsll((long long)dj) - 1;
+                                dj &= dj - 1;
+                                record(i, j, 2 * level);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < nt && s_nfound[threadIdx.x] >= nt - 1) atomicAnd(&s_active, ~(1ull << threadIdx.x));
             if (threadIdx.x == 0) s_nf[cb] = 0;
             cb ^= 1;
             const bool done = s_pairs >= want || nn == 0;
@@ -147,11 +196,10 @@ specificity_kernel(const long long* __restrict__ indptr, const int32_t* __restri
             const int v = sc.touched[f];
             sc.cur[v] = 0ull;
             sc.acc[v] = 0ull;
-            sc.tpos[v] = 0;
         }
         if (threadIdx.x == 0) {
-            out_sum[t] = (long long)s_sum;
-            out_pairs[t] = s_pairs;
+            out_sum[t] = 2 * (long long)s_sum;          // ordered-pair convention of the interface
+            out_pairs[t] = 2 * s_pairs;
             out_nmapped[t] = nt;
             s_nf[0] = 0;
             s_nf[1] = 0;
