@@ -368,3 +368,36 @@ def test_connected_components_match_scipy(core, n, deg, seed):
     for i, (x, y) in enumerate(zip(lab, ref)):
         assert first.setdefault(y, x) == x
     assert all(lab[x] == x for x in np.unique(lab)) and (lab <= np.arange(n)).all()
+
+
+@pytest.mark.parametrize("shape", ["path", "cycle", "star", "tree", "grid", "clique"])
+def test_mapping_specificity_structured_graphs(core, shape):
+    """Odd and even pair distances, long paths, hubs: the lock-step meeting rule (2L - 1 when a bit joins a node
+    that already holds the other, 2L when both arrive together) must give networkx's distances exactly."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(len(shape))
+    if shape == "path":
+        m = 90; a = np.arange(m - 1); b = a + 1
+    elif shape == "cycle":
+        m = 77; a = np.arange(m); b = (a + 1) % m
+    elif shape == "star":
+        m = 200; a = np.zeros(m - 1, dtype=int); b = np.arange(1, m)
+    elif shape == "tree":
+        m = 255; b = np.arange(1, m); a = (b - 1) // 2
+    elif shape == "grid":
+        side = 17; m = side * side
+        idx = np.arange(m).reshape(side, side)
+        a = np.r_[idx[:, :-1].ravel(), idx[:-1, :].ravel()]; b = np.r_[idx[:, 1:].ravel(), idx[1:, :].ravel()]
+    else:
+        m = 40; a, b = np.triu_indices(m, 1)
+    adj = sp.coo_matrix((np.ones(2 * len(a), np.int8), (np.r_[a, b], np.r_[b, a])), shape=(m, m)).tocsr()
+    adj.sum_duplicates()
+    n, k = 120, 9
+    knn = np.stack([rng.choice(m, k, replace=False) for _ in range(n)]).astype(np.int32)
+    knn[0] = np.array([0, m - 1, m // 2, 1, m - 2, m // 3, 2, m - 3, m // 4])[:k]      # the extremes together
+    cnt = (rng.random((n, k)) < 0.8).astype(np.uint8)
+    cnt[0] = 1
+    mean, connected = core.mapping_specificity(adj.indptr.astype(np.int64), adj.indices.astype(np.int32), knn, cnt)
+    assert connected.all()
+    exp = O.mapping_specificity(a, b, m, knn, cnt)
+    assert np.array_equal(mean, exp, equal_nan=True)
