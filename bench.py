@@ -464,6 +464,8 @@ def run_b200(a):
                                 "ms_per_step": sec["ms_total"] / sec_steps, "kernel_ms_per_step": sk,
                                 "rows_exact_fallback_per_step": sec["fallback"] / sec_steps,
                                 "roofline": canberra_roofline(g, N, M, sk)}
+        if os.path.exists(tr):
+            line["mod_canberra"]["roofline"]["traffic"] = json.load(open(tr)).get("cbs::sliced_kernel")
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline and a.metric != "cosine":
         threads = os.cpu_count() or 1
