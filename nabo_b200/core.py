@@ -9,12 +9,11 @@ computation is a call into ``libnabo_b200.so``.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional
 
 import numpy as np
 import torch
 
-from . import _lib
 from ._lib import METRICS, MODE_EXACT, MODE_FAST, check, lib, require_device
 
 __all__ = ["euclidean_dist", "mod_canberra_dist", "cosine_dist", "knn", "knn_candidates", "rerank_exact", "merge_topk",

@@ -30,7 +30,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from . import core
-from .store import batched_writes, Group, RowGroup, open_file
+from .store import batched_writes, RowGroup, open_file
 
 __all__ = ["Mapping", "read_matrix"]
 

@@ -20,7 +20,6 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Tuple
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -9,7 +9,7 @@ from; fixtures carry a SHA-256 of the inputs to prove it.
 from __future__ import annotations
 
 import hashlib
-from typing import List, Tuple
+from typing import List
 
 import numpy as np
 
