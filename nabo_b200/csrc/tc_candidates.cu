@@ -235,15 +235,22 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid
 }
 
 // work item w -> (query item, first / last reference tile of its range)
+template <bool SPLIT>
 __device__ __forceinline__ void decode_item(const Params& p, int w, int& qitem, int& seg, int& j0, int& j1) {
+    if (!SPLIT) {                      // one piece: the instantiation the large-N path runs is the unsplit kernel
+        qitem = w; seg = 0; j0 = 0; j1 = p.n_rtiles;
+        return;
+    }
     qitem = w / p.n_split;
     seg = w - qitem * p.n_split;
     j0 = (int)((long long)p.n_rtiles * seg / p.n_split);
     j1 = (int)((long long)p.n_rtiles * (seg + 1) / p.n_split);
 }
 
-template <int KSTEPS>   // K steps of 16 known at compile time (0 = runtime loop)
+template <int KSTEPS, bool SPLIT>   // K steps of 16 known at compile time (0 = runtime loop); SPLIT: n_split > 1
 __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p) {
+    const int n_work = SPLIT ? p.n_items * p.n_split : p.n_items;
+    const int n_seg = SPLIT ? p.n_split : 1;
     extern __shared__ __align__(1024) uint8_t smem[];
     Barriers* bars = reinterpret_cast<Barriers*>(smem + p.bar_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -268,9 +275,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t t = 0, it = 0;
-            for (int w = blockIdx.x; w < p.n_items * p.n_split; w += gridDim.x, ++it) {
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
                 int item, seg, j0, j1;
-                decode_item(p, w, item, seg, j0, j1);
+                decode_item<SPLIT>(p, w, item, seg, j0, j1);
                 ptx::mbar_wait(&bars->a_empty, (it & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&bars->a_full, NQ * a_tile_bytes);
                 for (int q = 0; q < NQ; ++q) {
@@ -305,9 +312,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
             const uint64_t ad0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.a_off), lbo, sbo);
             const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off), lbo, sbo);
             uint32_t t = 0, it = 0, n = 0;
-            for (int w = blockIdx.x; w < p.n_items * p.n_split; w += gridDim.x, ++it) {
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
                 int item, seg, j0, j1;
-                decode_item(p, w, item, seg, j0, j1);
+                decode_item<SPLIT>(p, w, item, seg, j0, j1);
                 ptx::mbar_wait(&bars->a_full, it & 1);
                 for (int j = j0; j < j1; ++j, ++t) {
                     const uint32_t s = t % p.stages, use = t / p.stages;
@@ -358,9 +365,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
             const uint64_t ad0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.a_off) + q * a_tile_bytes, lbo, sbo);
             const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off), lbo, sbo);
             uint32_t t = 0, it = 0;
-            for (int w = blockIdx.x; w < p.n_items * p.n_split; w += gridDim.x, ++it) {
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
                 int item, seg, j0, j1;
-                decode_item(p, w, item, seg, j0, j1);
+                decode_item<SPLIT>(p, w, item, seg, j0, j1);
                 ptx::mbar_wait(&bars->a_full, it & 1);
                 for (int j = j0; j < j1; ++j, ++t) {
                     const uint32_t s = t % p.stages, use = t / p.stages;
@@ -399,9 +406,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         uint32_t t = 0;
         uint32_t ks[4], kpl[4];
         uint32_t* hist = reinterpret_cast<uint32_t*>(smem + p.sort_off) + (size_t)warp * 256;
-        for (int w = blockIdx.x; w < p.n_items * p.n_split; w += gridDim.x) {
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             int item, seg, j0, j1;
-            decode_item(p, w, item, seg, j0, j1);
+            decode_item<SPLIT>(p, w, item, seg, j0, j1);
             float tau = CUDART_INF_F;
             int cnt = 0;
             for (int j = j0; j < j1; ++j, ++t) {
@@ -457,7 +464,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                     for (int u = 0; u < 4; ++u) {
                         const int i = u * 32 + lane;
                         if (i < p.kc_out)
-                            p.cand_idx[(qg * p.n_split + seg) * p.kc_out + i] = i < nc ? (int32_t)kpl[u] : -1;
+                            p.cand_idx[(qg * n_seg + seg) * p.kc_out + i] = i < nc ? (int32_t)kpl[u] : -1;
                     }
                     if (lane == 0) p.cert_tau[(long long)seg * p.n_query + qg] = n >= p.kprime ? nt : old_tau;
                 }
@@ -582,9 +589,15 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     p.soft = tc::CAP - tc::CHUNK - 16 > kprime ? tc::CAP - tc::CHUNK - 16 : kprime;
 #define NABO_TC_LAUNCH(KS)                                                                                          \
     do {                                                                                                           \
-        NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                       (int)pl.total));                                                            \
-        tc::candidates_kernel<KS><<<grid, tc::NTHREADS, pl.total, st>>>(p);                                        \
+        if (n_split > 1) {                                                                                         \
+            NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel<KS, true>,                                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));           \
+            tc::candidates_kernel<KS, true><<<grid, tc::NTHREADS, pl.total, st>>>(p);                              \
+        } else {                                                                                                   \
+            NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel<KS, false>,                                       \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));           \
+            tc::candidates_kernel<KS, false><<<grid, tc::NTHREADS, pl.total, st>>>(p);                             \
+        }                                                                                                          \
     } while (0)
     if (kp == 160) NABO_TC_LAUNCH(10);        // g = 50 (BASELINE configs 2-5)
     else if (kp == 80) NABO_TC_LAUNCH(5);     // g = 25 (config 1)
