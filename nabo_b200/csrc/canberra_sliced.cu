@@ -199,7 +199,7 @@ struct Params {
     const float* rt;            // [n_tiles64][g][64]
     const float* qx;            // [n_groups][g][32]
     const uint32_t* ctrl;       // [n_groups][nj][32]
-    int n_query, n_ref, g, n_tiles, n_tiles64, n_groups, kprime, stages, nj;
+    int n_query, n_ref, g, n_tiles, n_tiles64, n_groups, kprime, stages, nj, n_split;
     float fm;
     int trig_extra;
     unsigned long long* cand_buf;   // [gridDim][QB][CAP]
@@ -232,7 +232,7 @@ __device__ __forceinline__ int need_of(float tau, int g) {
     return c > 63 ? 63 : c;
 }
 
-template <int NB>
+template <int NB, bool SPLIT>      // SPLIT: the CTAs of one query block share out the reference range (n_split > 1)
 __global__ void __launch_bounds__(NTHREADS, 1)
 sliced_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -243,18 +243,27 @@ sliced_kernel(const Params p) {
     // Work = 32-query groups, dealt evenly to the CTAs; a CTA sweeps the reference once per round with
     // as many of its warps busy as it has groups left (balanced over the rounds).  Dealing whole
     // NW-group items instead would leave most SMs idle whenever n_query / (32 NW) is not a multiple of the grid.
-    const int g_begin = (int)((long long)p.n_groups * blockIdx.x / gridDim.x);
-    const int n_mine = (int)((long long)p.n_groups * (blockIdx.x + 1) / gridDim.x) - g_begin;
+    // With few groups (a CTA would keep one or two warps busy, and a warp's sweep is latency-bound) the
+    // reference range is cut into n_split pieces: CTA b sweeps piece b % n_split for query block b / n_split,
+    // each piece yields its own K' list and threshold, the re-rank takes their union / minimum.
+    const int n_seg = SPLIT ? p.n_split : 1;
+    const int seg = SPLIT ? (int)(blockIdx.x % (unsigned)n_seg) : 0;
+    const int qblock = SPLIT ? (int)(blockIdx.x / (unsigned)n_seg) : (int)blockIdx.x;
+    const int n_qblocks = SPLIT ? (int)(gridDim.x / (unsigned)n_seg) : (int)gridDim.x;
+    const int tile0 = SPLIT ? (int)((long long)p.n_tiles * seg / n_seg) : 0;
+    const int n_tiles = SPLIT ? (int)((long long)p.n_tiles * (seg + 1) / n_seg) - tile0 : p.n_tiles;
+    const int g_begin = (int)((long long)p.n_groups * qblock / n_qblocks);
+    const int n_mine = (int)((long long)p.n_groups * (qblock + 1) / n_qblocks) - g_begin;
     const int rounds = (n_mine + NW - 1) / NW;
     const int wpr = rounds > 0 ? (n_mine + rounds - 1) / rounds : 0;      // busy warps per round
-    const uint32_t total_tiles = (uint32_t)rounds * (uint32_t)p.n_tiles;
+    const uint32_t total_tiles = (uint32_t)rounds * (uint32_t)n_tiles;
 
     // Reference tiles arrive by TMA bulk copies into a ring of p.stages buffers (full[] mbarriers).  There
     // is no producer warp: every warp counts itself out of a stage when it is done with the tile, and the
     // last one out re-arms the stage with the tile p.stages ahead - the earliest moment it can be issued.
     const uint32_t plane_bytes = (uint32_t)((size_t)g * WPT * NPL * 4);
     auto issue_tile = [&](uint32_t tn, uint32_t s) {          // one thread
-        const int j = (int)(tn % (uint32_t)p.n_tiles);
+        const int j = tile0 + (int)(tn % (uint32_t)n_tiles);
         const int n64 = min(2, p.n_tiles64 - 2 * j);
         const uint32_t ys_bytes = (uint32_t)n64 * g * 64 * 4;
         ptx::mbar_arrive_expect_tx(&bars->full[s], plane_bytes + ys_bytes);
@@ -341,7 +350,7 @@ sliced_kernel(const Params p) {
         const int gi = round * wpr + warp;
         if (warp >= wpr || gi >= n_mine) {
             // no group for this warp in this round: keep the tile ring moving
-            for (int j = 0; j < p.n_tiles; ++j, ++t) {
+            for (int j = 0; j < n_tiles; ++j, ++t) {
                 const uint32_t s = t % p.stages, use = t / p.stages;
                 ptx::mbar_wait(&bars->full[s], use & 1);
                 release_tile(t, s);
@@ -358,7 +367,8 @@ sliced_kernel(const Params p) {
         s_cnt[lane] = 0;
         __syncwarp();
 
-        for (int j = 0; j < p.n_tiles; ++j, ++t) {
+        for (int jl = 0; jl < n_tiles; ++jl, ++t) {
+            const int j = tile0 + jl;
             const uint32_t s = t % p.stages, use = t / p.stages;
             ptx::mbar_wait(&bars->full[s], use & 1);
             const unsigned char* stage = smem + p.stage_off + (size_t)s * p.stage_bytes;
@@ -496,9 +506,9 @@ sliced_kernel(const Params p) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int i = u * 32 + lane;
-                    if (i < kprime) p.cand[qg * kprime + i] = i < nc ? (int32_t)kpl[u] : -1;
+                    if (i < kprime) p.cand[(qg * n_seg + seg) * kprime + i] = i < nc ? (int32_t)kpl[u] : -1;
                 }
-                if (lane == 0) p.tau_out[qg] = n >= kprime ? nt : old_tau;
+                if (lane == 0) p.tau_out[(long long)seg * p.n_query + qg] = n >= kprime ? nt : old_tau;
             }
         }
         __syncwarp();
@@ -535,16 +545,32 @@ size_t nabo_cbs_extra_bytes(int n_query, int n_ref, int g) {
 }
 
 // rt: FP32 pre-tiled reference ([tile64][k][64], nabo_cb_pretile_floats(n_ref, g) floats), filled here.
+// Pieces the reference range is cut into (see the kernel): only when a CTA would have at most four busy warps,
+// never below 64 tiles (8 192 references) per piece, and the union of the K' lists must fit the re-rank (128).
+int nabo_cbs_split(int n_query, int n_ref, int k, int drop_first) {
+    const int n_groups = (n_query + 31) / 32;
+    const int n_tiles = (n_ref + cbs::RT - 1) / cbs::RT;
+    const int per_cta = (n_groups + cbs_grid(1 << 30) - 1) / cbs_grid(1 << 30);
+    int s = per_cta > 0 ? cbs::NW / per_cta : 1;
+    if (s > NABO_CBS_MAX_SPLIT) s = NABO_CBS_MAX_SPLIT;
+    while (s > 1 && (n_tiles / s < 64 || s * nabo_cb_kprime(k, drop_first) > 128)) --s;
+    return s < 1 ? 1 : s;
+}
+
+// cand: [n_query][n_split][K'], tau: [n_split][n_query]
 int nabo_cbs_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
-                        double f, const uint8_t* mask, int drop_first, float* rt, void* extra, size_t extra_bytes,
-                        int32_t* cand, float* tau, cudaStream_t st) {
+                        double f, const uint8_t* mask, int drop_first, int n_split, float* rt, void* extra,
+                        size_t extra_bytes, int32_t* cand, float* tau, cudaStream_t st) {
     const int kprime = nabo_cb_kprime(k, drop_first);
+    if (n_split < 1 || n_split > NABO_CBS_MAX_SPLIT) n_split = 1;
     const cbs::SmemPlan pl = cbs::plan_smem(g);
     const int n_tiles = (n_ref + cbs::RT - 1) / cbs::RT;
     const int n_tiles64 = (n_ref + 63) / 64;
     const size_t n_groups = (size_t)(n_query + 31) / 32;
     const int nb = cbs::nblocks8(g), nj = nb * 4;
-    const int grid = cbs_grid((int)n_groups);
+    int grid = cbs_grid((int)n_groups * n_split);
+    if (n_split > 1) grid = grid / n_split * n_split;      // whole query blocks
+    if (grid < n_split) n_split = 1, grid = cbs_grid((int)n_groups);
 
     NaboArena ar(extra, extra_bytes);
     uint32_t* planes = (uint32_t*)ar.take<char>((size_t)n_tiles * cbs::plane_tile_bytes(g));
@@ -569,7 +595,7 @@ int nabo_cbs_candidates(const double* q, int ldq, const double* r, int ldr, int 
     cbs::Params p;
     p.planes = planes; p.rt = rt; p.qx = qx; p.ctrl = ctrl;
     p.n_query = n_query; p.n_ref = n_ref; p.g = g; p.n_tiles = n_tiles; p.n_tiles64 = n_tiles64;
-    p.n_groups = (int)n_groups; p.kprime = kprime; p.stages = pl.stages; p.nj = nj;
+    p.n_groups = (int)n_groups; p.kprime = kprime; p.stages = pl.stages; p.nj = nj; p.n_split = n_split;
     const double delta = fmax(1e-5, 4e-7 * (2.0 + f) / f);      // same optimistic margin as canberra_candidates.cu
     p.fm = (float)(f * (1.0 + delta));
     p.cand_buf = cbuf; p.cand = cand; p.tau_out = tau;
@@ -578,9 +604,15 @@ int nabo_cbs_candidates(const double* q, int ldq, const double* r, int ldr, int 
     p.work_off = pl.work_off; p.tau_off = pl.tau_off; p.cnt_off = pl.cnt_off; p.bar_off = pl.bar_off;
 #define NABO_CBS_LAUNCH(NBV)                                                                                       \
     case NBV:                                                                                                      \
-        NABO_CUDA(cudaFuncSetAttribute(cbs::sliced_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                       (int)pl.total));                                                            \
-        cbs::sliced_kernel<NBV><<<grid, cbs::NTHREADS, pl.total, st>>>(p);                                         \
+        if (n_split > 1) {                                                                                         \
+            NABO_CUDA(cudaFuncSetAttribute(cbs::sliced_kernel<NBV, true>,                                          \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));           \
+            cbs::sliced_kernel<NBV, true><<<grid, cbs::NTHREADS, pl.total, st>>>(p);                               \
+        } else {                                                                                                   \
+            NABO_CUDA(cudaFuncSetAttribute(cbs::sliced_kernel<NBV, false>,                                         \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));           \
+            cbs::sliced_kernel<NBV, false><<<grid, cbs::NTHREADS, pl.total, st>>>(p);                              \
+        }                                                                                                          \
         break;
     switch (nb) {
         NABO_CBS_LAUNCH(1) NABO_CBS_LAUNCH(2) NABO_CBS_LAUNCH(3) NABO_CBS_LAUNCH(4)

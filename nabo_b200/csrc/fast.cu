@@ -16,7 +16,8 @@ static size_t cb_extra_bytes(int n_query, int n_ref, int g) {
 
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric) {
     if (metric == NABO_MOD_CANBERRA)
-        return nabo_align_up((size_t)n_query * nabo_cb_kprime(k, 1) * 4, 256) + 3 * nabo_align_up((size_t)n_query * 4, 256) +
+        return nabo_align_up((size_t)n_query * nabo_cb_kprime(k, 1) * 4 * NABO_CBS_MAX_SPLIT, 256) +
+               (2 + NABO_CBS_MAX_SPLIT) * nabo_align_up((size_t)n_query * 4, 256) +
                nabo_align_up(nabo_cb_pretile_floats(n_query, g) * 4, 256) + nabo_align_up(nabo_cb_pretile_floats(n_ref, g) * 4, 256) +
                nabo_align_up(nabo_exact_split_workspace(k + 1), 256) + nabo_align_up(cb_extra_bytes(n_query, n_ref, g), 256) + 4096;
     return nabo_tc_workspace_bytes(n_query, n_ref, g, k, 1) + nabo_align_up((size_t)n_query * 4, 256) +
@@ -38,8 +39,10 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
             return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
         NaboArena ar(workspace, workspace_bytes);
         const int kprime = nabo_cb_kprime(k, drop_first);
-        int32_t* cand = ar.take<int32_t>((size_t)n_query * kprime);
-        float* tau = ar.take<float>(n_query);
+        const bool sliced_ok = nabo_cbs_supported(g, k, drop_first) && f >= 1e-6;
+        const int n_split = sliced_ok ? nabo_cbs_split(n_query, n_ref, k, drop_first) : 1;
+        int32_t* cand = ar.take<int32_t>((size_t)n_query * kprime * n_split);
+        float* tau = ar.take<float>((size_t)n_query * n_split);
         int* fail_rows = ar.take<int>(n_query);
         int* fail_count = ar.take<int>(1);
         float* qt = ar.take<float>(nabo_cb_pretile_floats(n_query, g));
@@ -50,18 +53,22 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
         NABO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
         // the interval ends of the sliced pass carry a 1e-6 relative margin over f|x|; it must dominate the FP64
         // rounding of x -+ f|x| (~1e-16 |x|), so a vanishing dist_factor goes to the FP16 two-phase pass instead
-        const bool sliced = nabo_cbs_supported(g, k, drop_first) && f >= 1e-6;
+        const bool sliced = sliced_ok;
         int rc = sliced
-                     ? nabo_cbs_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, rt, extra,
+                     ? nabo_cbs_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, n_split, rt, extra,
                                            cb_extra_bytes(n_query, n_ref, g), cand, tau, st)
                      : nabo_cb_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, qt, rt, extra, cand,
                                           tau, st);
         if (rc) return rc;
+        if (n_split > 1) {
+            rc = nabo_tau_min_launch(tau, n_query, n_split, st);
+            if (rc) return rc;
+        }
         tm.end(0);
         NaboCert cert;
         cert.kind = NABO_CERT_LINEAR; cert.tau = tau; cert.qn2 = nullptr; cert.scal = nullptr; cert.c_acc = nabo_cb_eps(g);
         rc = nabo_rerank_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset, cand,
-                                kprime, cert, fail_rows, fail_count, out_idx, out_dist, st);
+                                kprime * n_split, cert, fail_rows, fail_count, out_idx, out_dist, st);
         if (rc) return rc;
         tm.end(1);
         rc = nabo_knn_exact_fallback(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,

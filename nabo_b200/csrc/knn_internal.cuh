@@ -70,9 +70,12 @@ int nabo_cb_pretile_launch(const double* x, int ld, int n, int g, float* out, cu
 // bit-sliced Canberra pass (canberra_sliced.cu); same outputs as nabo_cb_candidates
 bool nabo_cbs_supported(int g, int k, int drop_first);
 size_t nabo_cbs_extra_bytes(int n_query, int n_ref, int g);
+#define NABO_CBS_MAX_SPLIT 3
+int nabo_cbs_split(int n_query, int n_ref, int k, int drop_first);
 int nabo_cbs_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
-                        double f, const uint8_t* mask, int drop_first, float* rt, void* extra, size_t extra_bytes,
-                        int32_t* cand, float* tau, cudaStream_t st);
+                        double f, const uint8_t* mask, int drop_first, int n_split, float* rt, void* extra,
+                        size_t extra_bytes, int32_t* cand, float* tau, cudaStream_t st);
+int nabo_tau_min_launch(float* tau, int n_query, int n_split, cudaStream_t st);
 
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric);
 int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,

@@ -525,6 +525,12 @@ __global__ void tau_min_kernel(float* __restrict__ tau, int n_query, int n_split
     tau[i] = t;
 }
 
+int nabo_tau_min_launch(float* tau, int n_query, int n_split, cudaStream_t st) {
+    tau_min_kernel<<<(n_query + 255) / 256, 256, 0, st>>>(tau, n_query, n_split);
+    NABO_LAUNCH_CHECK("tau_min_kernel");
+    return 0;
+}
+
 size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_first) {
     const int kp = tc::kp_for(g);
     const size_t tb = tc::tile_bytes(kp);
@@ -605,8 +611,8 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
 #undef NABO_TC_LAUNCH
     NABO_LAUNCH_CHECK("candidates_kernel");
     if (n_split > 1) {
-        tau_min_kernel<<<(n_query + 255) / 256, 256, 0, st>>>(tau, n_query, n_split);
-        NABO_LAUNCH_CHECK("tau_min_kernel");
+        int rc = nabo_tau_min_launch(tau, n_query, n_split, st);
+        if (rc) return rc;
         *launches += 1;
     }
     tm.end(0);
