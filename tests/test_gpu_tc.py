@@ -220,3 +220,26 @@ def test_canberra_sliced_degenerate_values(core):
     si, sd = core.knn(r[:2000], r[:2000], k, "mod_canberra", 0.25, drop_first=True, mode="fast")
     ei, ed = core.knn(r[:2000], r[:2000], k, "mod_canberra", 0.25, drop_first=True, mode="exact")
     assert same_bits(sd, ed) and np.array_equal(si, ei)
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "mod_canberra"])
+@pytest.mark.parametrize("n,m", [(700, 20000), (3000, 40000), (9000, 30000)])
+def test_reference_split_for_small_query_sets(core, metric, n, m):
+    """Few queries: the candidate kernels cut the reference range into pieces swept by different CTAs and the
+    re-rank takes the union of the pieces' K' lists with the smallest threshold.  Same result as the exact engine,
+    with masks, duplicates, drop_first and an index offset, and the rows must still certify."""
+    from nabo_b200 import synth
+    rng = np.random.default_rng(n + m)
+    r = synth.pc_mixture(m, 50, seed=1)
+    q = synth.pc_mixture(n, 50, seed=2)
+    r[rng.integers(0, m, 50)] = r[7]                       # ties that straddle the pieces
+    q[:20] = r[rng.integers(0, m, 20)]
+    mask = rng.random(m) < 0.1
+    for kw in (dict(), dict(ref_mask=mask, idx_offset=5)):
+        fi, fd, st = core.knn(q, r, 30, metric, 0.25, mode="fast", return_stats=True, **kw)
+        ei, ed = core.knn(q, r, 30, metric, 0.25, mode="exact", **kw)
+        assert same_bits(fd, ed) and np.array_equal(fi, ei)
+        assert st["rows_exact_fallback"] <= max(60, n // 20)
+    si, sd = core.knn(r[:n], r, 15, metric, 0.25, drop_first=True, mode="fast")
+    ei, ed = core.knn(r[:n], r, 15, metric, 0.25, drop_first=True, mode="exact")
+    assert same_bits(sd, ed) and np.array_equal(si, ei)
