@@ -54,6 +54,9 @@ def parse():
                          "reference, all GPUs map the same --n-query targets, candidates are all-gathered and merged "
                          "(BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-sharded", action="store_true", help="skip the reference-sharded (config 4) block")
+    ap.add_argument("--ref-rows-per-gpu", type=int, default=1_250_000)
+    ap.add_argument("--ref-batch", type=int, default=200_000, help="targets per step of the reference-sharded block")
     ap.add_argument("--no-secondary", action="store_true", help="skip the modified-Canberra measurement")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per cpu_baseline sample")
     return ap.parse_args()
@@ -215,14 +218,190 @@ def run_reference_arm(a):
 
 
 # ----------------------------------------------------------------------------- B200 arm, reference-sharded
-def run_b200_refshard(a):
-    """BASELINE config 4 shape: the reference is split by rows over the GPUs (--n-ref rows each), every GPU maps
-    the same --n-query targets against its rows, the (distance, global index) candidates are all-gathered over
-    NCCL and merged (nabo_merge_topk), then SNN weights and all-reduced mapping scores."""
-    import numpy as np
+def _ev_ms(pairs):
+    return [s.elapsed_time(e) for s, e in pairs]
+
+
+def ref_sharded_block(a, dev, rank, world, rows_per_gpu, n_batch, n_batches, steps, warmup, metric="euclidean",
+                      check_rows=1024):
+    """BASELINE config 4 (the north-star shape at 8 GPUs): a reference of world x rows_per_gpu cells split by rows,
+    every rank maps the same batches of targets against its rows; the re-rank kernel delivers each result row to
+    the rank that owns the target (peer memory over NVLink, or one all_to_all_single), which merges the per-source
+    lists in place, computes the SNN weights against the replicated TRUE reference kNN table and adds its integer
+    weight sums to the all-reduced per-reference score accumulator.  One step = one batch of n_batch targets.
+    Untimed, in the same run: the merged (idx, dist) of check_rows sampled targets is compared bit for bit with
+    the unsharded exact engine over the whole reference on rank 0."""
     import torch
     import torch.distributed as dist
-    from nabo_b200 import build, core, parallel, synth
+    from nabo_b200 import core, parallel, synth
+
+    g, k = a.comps, a.k
+    M = rows_per_gpu
+    m_total = M * world
+    t_setup = time.perf_counter()
+    ref = synth.pc_mixture_device(M, g, seed=1 + 1000 * rank, device=dev)            # this rank's rows
+    if world > 1:
+        full = torch.empty((m_total, g), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(full, ref)
+    else:
+        full = ref
+    # the replicated reference kNN table (make_ref_graph's sorted rows), built by the same sharded path:
+    # every rank queries all cells against its rows, self dropped after the global merge
+    ref_knn = torch.empty((m_total, k), dtype=torch.int32, device=dev)
+    chunk = n_batch
+    for lo in range(0, m_total, chunk):
+        hi = min(m_total, lo + chunk)
+        _, _, ri, _ = parallel.knn_reference_sharded(full[lo:hi], ref, rank * M, k, "euclidean", drop_first=True,
+                                                     mode=a.engine, merge_slice=False)
+        ref_knn[lo:hi] = ri
+    batches = [synth.pc_mixture_device(n_batch, g, seed=101 + b, device=dev) for b in range(n_batches)]
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step(q, timings=None):
+        return parallel.map_reference_sharded(q, ref, rank * M, m_total, ref_knn, k, metric=metric, dist_factor=0.25,
+                                              mode=a.engine, timings=timings)
+
+    for i in range(warmup):
+        step(batches[i % n_batches])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record()
+        step(batches[i % n_batches])
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([sum(_ev_ms(ev))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / steps
+
+    # per-stage pass (untimed): CUDA events around the stages + the library's own events inside the kNN call
+    stages = {}
+    kstats = []
+    for i in range(min(steps, n_batches)):
+        flush.zero_()
+        step(batches[i], timings=stages)
+        r = core.knn(batches[i], ref, k, metric, 0.25, idx_offset=rank * M, mode=a.engine, return_stats=True)
+        kstats.append(r[2])
+    torch.cuda.synchronize()
+    stage_ms = {name: sum(_ev_ms(p)) / len(p) for name, p in stages.items()}
+    if kstats:
+        stage_ms["knn_candidates"] = sum(x["main_kernel_ms"] for x in kstats) / len(kstats)
+        stage_ms["knn_rerank"] = sum(x["rerank_ms"] for x in kstats) / len(kstats)
+        stage_ms["knn_prepare"] = sum(x["prep_ms"] for x in kstats) / len(kstats)
+        stage_ms["knn_exact_fallback"] = sum(x["fallback_ms"] for x in kstats) / len(kstats)
+    st = torch.tensor([stage_ms.get(n_, 0.0) for n_ in sorted(stage_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    stage_ms = {n_: float(v) for n_, v in zip(sorted(stage_ms), st.tolist())}
+
+    # in-run parity (untimed): sampled targets of batch 0, sharded result vs the unsharded exact engine
+    out = step(batches[0])
+    sel = torch.linspace(0, n_batch - 1, check_rows, device=dev).long().unique()
+    mine = sel[(sel >= out["lo"]) & (sel < out["hi"])]
+    rows_i = out["idx"][mine - out["lo"]]
+    rows_d = out["dist"][mine - out["lo"]]
+    rows_w = out["weights"][mine - out["lo"]]
+    if world > 1:
+        sizes = [None] * world
+        dist.all_gather_object(sizes, int(mine.numel()))
+        pad = max(sizes)
+        def padded(x):
+            p = torch.zeros((pad,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
+            p[:x.shape[0]] = x
+            return p
+        gi = [torch.empty((pad, k), dtype=torch.int32, device=dev) for _ in range(world)]
+        gd = [torch.empty((pad, k), dtype=torch.float64, device=dev) for _ in range(world)]
+        gw = [torch.empty((pad, k), dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gi, padded(rows_i))
+        dist.all_gather(gd, padded(rows_d))
+        dist.all_gather(gw, padded(rows_w))
+        rows_i = torch.cat([x[:n_] for x, n_ in zip(gi, sizes)])
+        rows_d = torch.cat([x[:n_] for x, n_ in zip(gd, sizes)])
+        rows_w = torch.cat([x[:n_] for x, n_ in zip(gw, sizes)])
+    parity = None
+    if rank == 0:
+        xi, xd = core.knn(batches[0][sel], full, k, metric, 0.25, mode="exact")
+        _, xw = core.snn_weights(xi, ref_knn, k)
+        parity = {"rows": int(sel.numel()), "against": "unsharded exact engine (FP64 brute force) over all %d reference "
+                                                        "cells + SNN weights on the true reference kNN table" % m_total,
+                  "idx_equal": bool(torch.equal(rows_i, xi)),
+                  "dist_bit_equal": bool(torch.equal(rows_d.view(torch.int64), xd.view(torch.int64))),
+                  "weights_bit_equal": bool(torch.equal(rows_w.view(torch.int64), xw.view(torch.int64)))}
+        if not (parity["idx_equal"] and parity["dist_bit_equal"] and parity["weights_bit_equal"]):
+            raise SystemExit("ref_sharded parity check FAILED: %r" % (parity,))
+    ex = parallel._exchange_for(n_batch, k, dev, "auto")
+    peaks = load_peaks()
+    kern = stage_ms.get("knn_candidates", 0.0)
+    flops = 2.0 * g * n_batch * M
+    block = {
+        "workload": "config4: %d targets per step (%d batches = %d targets) x %d reference cells row-sharded over %d GPU(s) "
+                    "(%d rows each), %d PCs, k=%d, %s" % (n_batch, n_batches, n_batch * n_batches, m_total, world, M, g, k, metric),
+        "value": n_batch / (ms_step / 1e3), "unit": "cells/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
+        "targets_per_step": n_batch, "n_ref_total": m_total, "rows_per_gpu": M,
+        "pairs_per_s": float(n_batch) * m_total / (ms_step / 1e3),
+        "stage_ms": stage_ms,
+        "exchange": {"transport": ex.transport, "bytes_sent_per_rank_per_step": ex.bytes_sent(),
+                     "all_gather_equivalent_bytes_received": (world - 1) * n_batch * k * 12,
+                     "what": "(float64 distance, int32 global index) x k per target, written by rerank_kernel "
+                             "straight into the owner's receive block; merged in place by merge_kernel"},
+        "score_reduce": {"all_reduce_bytes": m_total * 8, "dtype": "int64 weight sums (hundredths)"},
+        "ref_knn": "true table: %d-cell self-kNN (k=%d) built in setup by the same sharded path" % (m_total, k),
+        "parity": parity, "setup_s": setup_s, "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "tc::candidates_kernel", "achieved": flops / (kern * 1e-3) / 1e12 if kern else None,
+                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": (flops / (kern * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]) if kern else None,
+                     "peak_source": "%s bf16 sustained (kernel timed inside a long step)" % peaks["source"],
+                     "executed_tflops": (flops * (((3 * g + 3 + 15) // 16 * 16) / g) / (kern * 1e-3) / 1e12) if kern else None,
+                     "traffic": None},
+    }
+    del full, ref_knn, batches, flush
+    torch.cuda.empty_cache()
+    return block
+
+
+def score_determinism_check(dev, rank, world, ref, ref_knn, k, n_targets=65_536):
+    """The same fixed problem (n_targets targets, the config-2 reference) mapped three ways - unsharded on one
+    GPU, target-sharded and reference-sharded over all ranks - must give the SAME per-reference score bits: the
+    score reduction is an integer sum (core.score_accumulate), so it does not depend on the GPU count.  The
+    SHA-256 of the score vector is reported; it is the same string at --gpus 1, 2, 4 and 8."""
+    import hashlib
+    import torch
+    from nabo_b200 import core, parallel, synth
+    M = ref.shape[0]
+    tgt = synth.pc_mixture_device(n_targets, ref.shape[1], seed=4242, device=dev)
+    ref_knn = ref_knn.contiguous()
+    i0, _ = core.knn(tgt, ref, k, "euclidean", mode="fast")
+    c0, _ = core.snn_weights(i0, ref_knn, k)
+    single = core.scores_finalize(core.score_accumulate(i0, c0, M, k), n_targets)
+    lo, hi = parallel.shard_bounds(n_targets, world, rank)
+    a_ = parallel.map_targets_sharded(tgt[lo:hi].contiguous(), ref, ref_knn, k, n_targets, metric="euclidean")
+    rlo, rhi = parallel.shard_bounds(M, world, rank)
+    b_ = parallel.map_reference_sharded(tgt, ref[rlo:rhi].contiguous(), rlo, M, ref_knn, k, metric="euclidean")
+    same = bool(torch.equal(single.view(torch.int64), a_["scores"].view(torch.int64)) and
+                torch.equal(single.view(torch.int64), b_["scores"].view(torch.int64)))
+    if not same:
+        raise SystemExit("score determinism check FAILED on rank %d" % rank)
+    return {"targets": n_targets, "n_ref": M, "bit_identical_single_vs_target_sharded_vs_reference_sharded": same,
+            "scores_sha256": hashlib.sha256(single.cpu().numpy().tobytes()).hexdigest()}
+
+
+def run_b200_refshard(a):
+    """`--shard reference`: only the reference-sharded block, as the whole line."""
+    import torch
+    import torch.distributed as dist
+    from nabo_b200 import build
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,82 +413,14 @@ def run_b200_refshard(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    g, k, M, N = a.comps, a.k, a.n_ref, a.n_query
-    m_total = M * world
-    ref = torch.from_numpy(synth.pc_mixture(M, g, seed=1 + 1000 * rank)).to(dev)        # this rank's rows
-    tgt_h = synth.pc_mixture(N, g, seed=101)                                             # same targets everywhere
-    tgt = torch.from_numpy(tgt_h).to(dev)
-    tgt_pin = torch.from_numpy(tgt_h).pin_memory()
-    # replicated reference kNN table with global indices; synthetic (uniform) - the SNN kernel's work does not
-    # depend on the values, and building the true table is an untimed set-up step of the same kNN kernels
-    ref_knn = torch.from_numpy(np.random.default_rng(7).integers(0, m_total, size=(m_total, k), dtype=np.int32)).to(dev)
-    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def step(q):
-        return parallel.map_reference_sharded(q, ref, rank * M, m_total, ref_knn, k, metric=a.metric,
-                                              dist_factor=0.25, mode=a.engine)
-
-    def timed(steps, warmup, e2e):
-        for _ in range(warmup):
-            step(tgt)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        sampler = ClockSampler(local)
-        sampler.start()
-        nbytes = [0, 0]
-        for i in range(steps):
-            flush.zero_()
-            ev[i][0].record()
-            if e2e:
-                out = step(tgt_pin.to(dev, non_blocking=True))
-                host = [out[key].cpu() for key in ("idx", "dist", "weights")]
-                nbytes = [tgt_pin.numel() * 8, sum(h.numel() * h.element_size() for h in host)]
-            else:
-                step(tgt)
-            ev[i][1].record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        clocks = sampler.stop()
-        t = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), clocks, nbytes
-
-    ms_total, clocks, _ = timed(a.steps, a.warmup, False)
-    e2e_steps = max(3, a.steps // 2)
-    e2e_ms, _, nb = timed(e2e_steps, 2, True)
-    ms_step = ms_total / a.steps
-    pairs = float(N) * m_total
-    peaks = load_peaks()
-    ach = 2.0 * g * N * M / (ms_step * 1e-3) / 1e12          # per GPU, whole step (not the kernel alone)
-    line = {
-        "metric": "target_cells_mapped_per_s", "value": N / (ms_step / 1e3), "unit": "cells/s", "n_gpus": world,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None,
-        "dtype": ("f64 (candidates: f16x2-split tcgen05, f32 accumulate)" if a.metric != "mod_canberra" else
-                  "f64 (candidates: bit-sliced u32 count bound, f32 evaluation)"),
-        "data": "synthetic",
-        "config": {"workload": "config4-shaped: %d targets x %d reference cells (%d rows per GPU), %d PCs, k=%d, %s"
-                               % (N, m_total, M, g, k, a.metric),
-                   "engine": a.engine, "sharding": "reference rows; all_gather_into_tensor of (idx, dist) + nabo_merge_topk; "
-                                                   "all_reduce of the scores",
-                   "ref_knn": "synthetic uniform table (values do not change the SNN kernel's work)",
-                   "l2": "512 MB buffer rewritten between timed iterations", "inputs_resident": True},
-        "clocks": clocks,
-        "e2e": {"value": N / (e2e_ms / e2e_steps / 1e3), "unit": "cells/s", "h2d_bytes_per_step": nb[0],
-                "d2h_bytes_per_step": nb[1], "ms_per_step": e2e_ms / e2e_steps,
-                "api": "nabo_b200.parallel.map_reference_sharded (pinned host targets in, this rank's result block out)"},
-        "gpu_launches": None,
-        "pairs_per_s": pairs / (ms_step * 1e-3),
-        "roofline": {"bound": "tensor", "kernel": "whole step per GPU (candidate pass + re-rank + merge + SNN + scores)",
-                     "achieved": ach, "unit": "TFLOP/s", "peak": peaks["bf16_tflops_sustained"],
-                     "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None},
-        "cpu_baseline": None,
-    }
+    b = ref_sharded_block(a, dev, rank, world, a.n_ref, a.n_query, 5, a.steps, a.warmup, metric=a.metric)
+    line = {"metric": "target_cells_mapped_per_s", "value": b["value"], "unit": "cells/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": b["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (candidates: f16x2-split tcgen05, f32 accumulate)",
+            "data": "synthetic", "config": {"workload": b["workload"], "engine": a.engine,
+                                            "l2": "512 MB buffer rewritten between timed iterations"},
+            "clocks": b["clocks"], "ref_sharded": b, "roofline": b["roofline"], "cpu_baseline": None,
+            "gpu_launches": None}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -344,11 +455,15 @@ def run_b200(a):
     ref_knn, _ = core.knn(ref, ref, k, "euclidean", drop_first=True, mode=a.engine)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    score_acc = torch.zeros(M, dtype=torch.int64, device=dev)
+
     def step(metric, q, stats=False):
         r = core.knn(q, ref, k, metric, 0.25, mode=a.engine, return_stats=stats)
         idx, dst = r[0], r[1]
         cnt, w = core.snn_weights(idx, ref_knn, k)
-        sc = core.mapping_scores(idx, cnt, M, k)
+        score_acc.zero_()
+        core.score_accumulate(idx, cnt, M, k, acc=score_acc)        # integer weight sums: same bits on any GPU count
+        sc = core.scores_finalize(score_acc, N)
         return idx, dst, cnt, w, sc, (r[2] if stats else None)
 
     def timed(metric, steps, warmup, e2e=False):
@@ -387,7 +502,7 @@ def run_b200(a):
                 flush.zero_()
                 st = step(metric, tgt, stats=True)[5]
                 kern_ms.append(st["main_kernel_ms"])
-                launches += st["kernel_launches"] + 1 + score_launches(M)
+                launches += st["kernel_launches"] + 1 + SCORE_LAUNCHES
                 fallback += st["rows_exact_fallback"]
             torch.cuda.synchronize()
         total_ms = sum(s.elapsed_time(e) for s, e in ev)
@@ -397,11 +512,7 @@ def run_b200(a):
         return {"ms_total": float(t.item()), "kern_ms": kern_ms, "launches": launches, "fallback": fallback,
                 "clocks": clocks, "wall_s": wall}
 
-    def score_launches(m):
-        bits = 1
-        while (1 << bits) <= m:
-            bits += 1
-        return 1 + 3 * ((bits + 7) // 8) + 1
+    SCORE_LAUNCHES = 3          # memset of the accumulator, score_accumulate_kernel, score_finalize_kernel
 
     def host_step(metric):
         """Public host-buffer API: pinned host targets in, pinned host results out (copies pipelined)."""
@@ -466,6 +577,12 @@ def run_b200(a):
                                 "roofline": canberra_roofline(g, N, M, sk)}
         if os.path.exists(tr):
             line["mod_canberra"]["roofline"]["traffic"] = json.load(open(tr)).get("cbs::sliced_kernel")
+
+    if not a.no_ref_sharded and a.metric == "euclidean" and a.engine == "fast":
+        # BASELINE config 4 under the same clock: world x 1.25 M reference rows, 5 batches of 200 k targets
+        line["ref_sharded"] = ref_sharded_block(a, dev, rank, world, a.ref_rows_per_gpu, a.ref_batch, 5,
+                                                max(5, a.steps // 2), 2)
+        line["score_determinism"] = score_determinism_check(dev, rank, world, ref, ref_knn, k)
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline and a.metric != "cosine":
         threads = os.cpu_count() or 1

@@ -113,6 +113,25 @@ int nabo_rerank_exact(const double* q, int ldq, const double* r, int ldr, int n_
 int nabo_merge_topk(const int32_t* idx, const double* dist, int n_shards, int n_query, int k,
                     int32_t* out_idx, double* out_dist, void* stream);
 
+/* The same merge with one (n_query x k) idx / dist block per shard at arbitrary device addresses
+ * (host tables of n_shards <= 16 pointers): the per-source blocks of an all-to-all or peer-written
+ * receive buffer are merged in place.  drop_first != 0 drops the first merged entry (the global
+ * "self" of a reference-sharded self-kNN) and writes k - 1 columns. */
+int nabo_merge_topk_parts(int n_shards, const int32_t* const* shard_idx_host,
+                          const double* const* shard_dist_host, int n_query, int k, int drop_first,
+                          int32_t* out_idx, double* out_dist, void* stream);
+
+/* nabo_knn with ROUTED result rows (reference-sharded mode): row t goes to part p with
+ * part_bounds_host[p] <= t < part_bounds_host[p+1] (n_parts + 1 ascending ints from 0 to n_query),
+ * at row t - bounds[p] of part_idx_host[p] / part_dist_host[p] ((rows_p x k) blocks, n_parts <= 16).
+ * The blocks may be slices of a local all-to-all send buffer or peer-GPU memory mapped over NVLink:
+ * the re-rank kernel that produces a row delivers it. */
+int nabo_knn_routed(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
+                    int k, int metric, double dist_factor, const uint8_t* ref_mask, int drop_first,
+                    int idx_offset, int mode, int n_parts, const int* part_bounds_host,
+                    int32_t* const* part_idx_host, double* const* part_dist_host, void* workspace,
+                    size_t workspace_bytes, int64_t* stats_host, void* stream);
+
 /* ---- (4) SNN neighbour weights: replaces _calc_snn ------------------------------
  * nabo/_mapping.py:151-200.  counts[t][j] = |set(tgt_knn[t]) & set(ref_knn[tgt_knn[t][j]])|
  * weights[t][j] = lut[counts] with lut[s] = round(s / (2(k-1) - s), 2) built on
@@ -134,6 +153,19 @@ int nabo_mapping_scores(const int32_t* tgt_knn, const uint8_t* counts, const dou
                         double min_weight, int weighted, double score_multiplier,
                         double min_score, double* out_scores, void* workspace,
                         size_t workspace_bytes, void* stream);
+
+/* GPU-count-independent form of the same score (sharded modes): the weight
+ * table in INTEGER units (int_weights[c], 0 = no edge / filtered; for the reference's table
+ * round(w, 2) * 100, exact) is accumulated per reference cell with integer atomics
+ * (acc int64 (n_ref), caller-zeroed, summed over batches / all-reduced over GPUs as integers),
+ * then score = score_multiplier * (acc / units_per_one) / n_include, zero below min_score.
+ * Same bits for any batch order and any number of GPUs; within 1e-14 relative of
+ * nabo_mapping_scores. */
+int nabo_score_accumulate(const int32_t* tgt_knn, const uint8_t* counts, const long long* int_weights,
+                          int n_query, int k, int n_ref, const uint8_t* include, long long* acc,
+                          void* stream);
+int nabo_scores_finalize(const long long* acc, int n_ref, double units_per_one, double score_multiplier,
+                         long long n_include, double min_score, double* out_scores, void* stream);
 
 /* Per-target cluster vote: array form of Graph.classify_target (nabo/_graph.py:722-792).
  * ref_labels int32 (n_ref), -1 = unlabelled; out_label -1 = na_label. */

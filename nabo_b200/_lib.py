@@ -41,6 +41,11 @@ SIGNATURES: Dict[str, tuple] = {
     "nabo_knn_candidates": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _z, _p]),
     "nabo_rerank_exact": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _d, _p, _i, _i, _p, _i, _p, _p, _p]),
     "nabo_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "nabo_merge_topk_parts": (_i, [_i, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "nabo_knn_routed": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _i, _d, _p, _i, _i, _i, _i, _p, _p, _p, _p, _z,
+                             C.POINTER(C.c_int64), _p]),
+    "nabo_score_accumulate": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "nabo_scores_finalize": (_i, [_p, _i, _d, _d, C.c_longlong, _d, _p, _p]),
     "nabo_snn_weights": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p]),
     "nabo_scores_workspace_bytes": (_z, [_i, _i, _i]),
     "nabo_mapping_scores": (_i, [_p, _p, _p, _i, _i, _i, _p, _i, _d, _i, _d, _d, _p, _p, _z, _p]),

@@ -17,7 +17,7 @@ import torch
 from ._lib import METRICS, MODE_EXACT, MODE_FAST, check, lib, require_device
 
 __all__ = ["euclidean_dist", "mod_canberra_dist", "cosine_dist", "knn", "knn_candidates", "rerank_exact", "merge_topk",
-           "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets", "mapping_specificity", "sparse_row_stats", "connected_components",
+           "merge_topk_parts", "snn_int_weights", "score_accumulate", "scores_finalize", "snn_weight_lut", "fix_weight", "snn_weights", "mapping_scores", "classify_targets", "mapping_specificity", "sparse_row_stats", "connected_components",
            "project", "project_csr", "scale_counts", "map_cells", "map_cells_host", "resolve_metric"]
 
 
@@ -126,13 +126,19 @@ def cosine_dist(x, y, d=None):
 
 # ----------------------------------------------------------------------------- (2) kNN
 def knn(q, r, k: int, metric: str = "euclidean", dist_factor: float = 0.25, ref_mask=None,
-        drop_first: bool = False, idx_offset: int = 0, mode: str = "fast", return_stats: bool = False, out=None):
+        drop_first: bool = False, idx_offset: int = 0, mode: str = "fast", return_stats: bool = False, out=None,
+        out_parts=None):
     """Fused distance + per-query top-k: what ``_calc_dist`` (nabo/_mapping.py:48-148) leaves
     for ``_calc_snn`` to read (``[:k]`` of each sorted row), without the N x M matrix.
 
     q (N,g), r (M,g) float64.  ``ref_mask`` (M,) bool marks ``ignore_ref_cells`` (sorted last,
     :135-140); ``drop_first`` is the reference<->reference ``[1:]`` (:141-142).
-    Returns (idx int32 (N,k), dist float64 (N,k)) [+ stats dict]."""
+    Returns (idx int32 (N,k), dist float64 (N,k)) [+ stats dict].
+
+    ``out_parts=(bounds, idx_ptrs, dist_ptrs)`` routes the result rows instead (``nabo_knn_routed``): row t
+    with bounds[p] <= t < bounds[p+1] is written to row t - bounds[p] of the (rows_p, k) int32 / float64
+    blocks at the device ADDRESSES idx_ptrs[p] / dist_ptrs[p] (local buffers or NVLink-mapped peer memory);
+    the call then returns (None, None)."""
     require_device()
     if metric not in METRICS:
         raise ValueError("ERROR: unknown metric %r" % (metric,))
@@ -150,6 +156,9 @@ def knn(q, r, k: int, metric: str = "euclidean", dist_factor: float = 0.25, ref_
     md = _mask_dev(ref_mask)
     if md is not None and md.numel() != m:
         raise ValueError("ERROR: ref_mask must have one entry per reference cell")
+    if out_parts is not None:
+        return _knn_routed(qd, rd, n, m, g, k, metric, dist_factor, md, drop_first, idx_offset, mode, out_parts,
+                           return_stats)
     if out is not None:                                    # caller-owned (n, k) int32 / float64 device buffers
         idx, dst = out
         if tuple(idx.shape) != (n, k) or tuple(dst.shape) != (n, k) or idx.dtype != torch.int32 or \
@@ -168,11 +177,34 @@ def knn(q, r, k: int, metric: str = "euclidean", dist_factor: float = 0.25, ref_
                      ws.numel(), stats, C.c_void_p(_stream())), "knn")
     res = (_out(idx, host), _out(dst, host))
     if return_stats:
-        res = res + ({"rows_reranked": int(stats[0]), "rows_exact_fallback": int(stats[1]),
-                      "candidates_per_row": int(stats[2]), "kernel_launches": int(stats[3]),
-                      "main_kernel_ms": stats[4] / 1e6, "rerank_ms": stats[5] / 1e6,
-                      "fallback_ms": stats[6] / 1e6, "prep_ms": stats[7] / 1e6},)
+        res = res + (_stats_dict(stats),)
     return res
+
+
+def _stats_dict(stats):
+    return {"rows_reranked": int(stats[0]), "rows_exact_fallback": int(stats[1]),
+            "candidates_per_row": int(stats[2]), "kernel_launches": int(stats[3]),
+            "main_kernel_ms": stats[4] / 1e6, "rerank_ms": stats[5] / 1e6,
+            "fallback_ms": stats[6] / 1e6, "prep_ms": stats[7] / 1e6}
+
+
+def _knn_routed(qd, rd, n, m, g, k, metric, dist_factor, md, drop_first, idx_offset, mode, out_parts, return_stats):
+    bounds, idx_ptrs, dist_ptrs = out_parts
+    n_parts = len(idx_ptrs)
+    if len(bounds) != n_parts + 1 or len(dist_ptrs) != n_parts:
+        raise ValueError("ERROR: out_parts needs n_parts + 1 bounds and n_parts idx / dist addresses")
+    mode_i = MODE_FAST if mode == "fast" else MODE_EXACT
+    L = lib()
+    ws_bytes = int(L.nabo_knn_workspace_bytes(n, m, g, k, METRICS[metric], mode_i))
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=qd.device)
+    stats = (C.c_int64 * 8)() if return_stats else None
+    b = (C.c_int * (n_parts + 1))(*[int(x) for x in bounds])
+    pi = (C.c_void_p * n_parts)(*[int(x) if x else None for x in idx_ptrs])
+    pd = (C.c_void_p * n_parts)(*[int(x) if x else None for x in dist_ptrs])
+    check(L.nabo_knn_routed(_ptr(qd), g, _ptr(rd), g, n, m, g, k, METRICS[metric], float(dist_factor), _ptr(md),
+                            1 if drop_first else 0, int(idx_offset), mode_i, n_parts, b, pi, pd, _ptr(ws), ws.numel(),
+                            stats, C.c_void_p(_stream())), "knn_routed")
+    return (None, None, _stats_dict(stats)) if return_stats else (None, None)
 
 
 def knn_candidates(q, r, k: int, metric: str = "euclidean", ref_mask=None, drop_first: bool = False):
@@ -231,6 +263,25 @@ def merge_topk(idx, dist, k: Optional[int] = None):
     check(lib().nabo_merge_topk(_ptr(i_d), _ptr(d_d), s, n, kk, _ptr(oi), _ptr(od), C.c_void_p(_stream())),
           "merge_topk")
     return _out(oi, host), _out(od, host)
+
+
+def merge_topk_parts(idx_ptrs, dist_ptrs, n_query: int, k: int, device, drop_first: bool = False, out=None):
+    """``nabo_merge_topk_parts``: merge one (n_query, k) idx / dist block per shard, given by device ADDRESS
+    (the per-source blocks of an all-to-all / peer-written receive buffer, consumed in place).
+    Returns (idx int32, dist float64) of shape (n_query, k - drop_first) on ``device``."""
+    require_device()
+    s = len(idx_ptrs)
+    ko = int(k) - (1 if drop_first else 0)
+    if out is not None:
+        oi, od = out
+    else:
+        oi = torch.empty((n_query, ko), dtype=torch.int32, device=device)
+        od = torch.empty((n_query, ko), dtype=torch.float64, device=device)
+    pi = (C.c_void_p * s)(*[int(x) for x in idx_ptrs])
+    pd = (C.c_void_p * s)(*[int(x) for x in dist_ptrs])
+    check(lib().nabo_merge_topk_parts(s, pi, pd, int(n_query), int(k), 1 if drop_first else 0, _ptr(oi), _ptr(od),
+                                      C.c_void_p(_stream())), "merge_topk_parts")
+    return oi, od
 
 
 # ----------------------------------------------------------------------------- (4) SNN weights
@@ -316,6 +367,64 @@ def mapping_scores(tgt_knn, counts, n_ref: int, k: Optional[int] = None, include
                                 float(min_weight), 1 if weighted else 0, float(score_multiplier),
                                 float(min_score), _ptr(out), _ptr(ws), ws.numel(), C.c_void_p(_stream())),
           "mapping_scores")
+    return _out(out, host)
+
+
+SCORE_UNITS = 100        # the reference's weights are round(w, 2): integers in hundredths
+
+
+def snn_int_weights(k: int, min_weight: float = 0.0, weighted: bool = True) -> np.ndarray:
+    """The SNN weight table in integer units for ``score_accumulate``: entry c = round(lut[c] * 100) (exact,
+    every weight is ``round(x, 2)``, nabo/_mapping.py:185, 194), 0 where the edge does not count
+    (c = 0, or weight <= min_weight, nabo/_graph.py:647-648); unweighted: 1 per counted edge (:649-650)."""
+    lut = snn_weight_lut(k)
+    iw = np.zeros(k + 1, dtype=np.int64)
+    for c in range(1, k + 1):
+        if weighted:
+            if lut[c] > min_weight:
+                iw[c] = int(round(lut[c] * SCORE_UNITS))
+                if abs(iw[c] / SCORE_UNITS - lut[c]) > 1e-12:
+                    raise ValueError("ERROR: weight table entry %r is not a multiple of 1/%d" % (lut[c], SCORE_UNITS))
+        else:
+            iw[c] = 1
+    return iw
+
+
+_IW_DEV: Dict[tuple, "torch.Tensor"] = {}
+
+
+def score_accumulate(tgt_knn, counts, n_ref: int, k: Optional[int] = None, acc=None, include=None,
+                     min_weight: float = 0.0, weighted: bool = True):
+    """Integer accumulation of the edge weights per reference cell (``nabo_score_accumulate``): adds this
+    batch of targets to ``acc`` (int64 (n_ref,), created zeroed when None) and returns it.  ``acc`` can be
+    summed over target batches and all-reduced over GPUs as integers: the resulting scores have the same bits
+    for any number of GPUs."""
+    require_device()
+    td, cd = _dev(tgt_knn, torch.int32), _dev(counts, torch.uint8)
+    n, kk = td.shape
+    k = kk if k is None else int(k)
+    key = (k, float(min_weight), bool(weighted), str(td.device))
+    iw = _IW_DEV.get(key)
+    if iw is None:
+        iw = _IW_DEV[key] = torch.from_numpy(snn_int_weights(k, min_weight, weighted)).to(td.device)
+    if acc is None:
+        acc = torch.zeros(int(n_ref), dtype=torch.int64, device=td.device)
+    inc = None if include is None else _mask_dev(include)
+    check(lib().nabo_score_accumulate(_ptr(td), _ptr(cd), _ptr(iw), n, kk, int(n_ref), _ptr(inc), _ptr(acc),
+                                      C.c_void_p(_stream())), "score_accumulate")
+    return acc
+
+
+def scores_finalize(acc, n_include: int, score_multiplier: float = 1000.0, min_score: float = 0.0,
+                    weighted: bool = True):
+    """score = score_multiplier * (acc / units) / n_include, zero below min_score (nabo/_graph.py:651-653, 690-693)."""
+    require_device()
+    host = _is_host(acc)
+    ad = _dev(acc, torch.int64)
+    out = torch.empty(ad.numel(), dtype=torch.float64, device=ad.device)
+    check(lib().nabo_scores_finalize(_ptr(ad), ad.numel(), float(SCORE_UNITS if weighted else 1),
+                                     float(score_multiplier), int(n_include), float(min_score), _ptr(out),
+                                     C.c_void_p(_stream())), "scores_finalize")
     return _out(out, host)
 
 
@@ -513,6 +622,7 @@ class _HostPipeline:
         self.dist = torch.empty((n, k), dtype=torch.float64, device=device)
         self.cnt = torch.empty((n, k), dtype=torch.uint8, device=device)
         self.w = torch.empty((n, k), dtype=torch.float64, device=device)
+        self.acc = torch.zeros(m, dtype=torch.int64, device=device)
         self.host = {"idx": torch.empty((n, k), dtype=torch.int32, pin_memory=True),
                      "dist": torch.empty((n, k), dtype=torch.float64, pin_memory=True),
                      "weights": torch.empty((n, k), dtype=torch.float64, pin_memory=True),
@@ -528,7 +638,8 @@ def map_cells_host(target_host: torch.Tensor, ref, ref_knn, k: int, metric: Opti
     """Host-buffer form of ``map_cells``: ``target_host`` is a pinned CPU float64 (N, g) tensor; the results
     land in pinned host tensors (idx, dist, weights, scores).  The targets are processed in ``chunks``
     pieces so that the host->device copy of piece i+1 and the device->host copy of piece i-1 overlap the
-    kernels of piece i (three CUDA streams); the per-reference scores are one reduction over all pieces."""
+    kernels of piece i (three CUDA streams); the per-reference scores are integer weight sums accumulated piece by
+    piece (``score_accumulate``), finalised once."""
     require_device()
     rd = _dev(ref, torch.float64)
     rk = _dev(ref_knn, torch.int32)
@@ -545,6 +656,7 @@ def map_cells_host(target_host: torch.Tensor, ref, ref_knn, k: int, metric: Opti
     bounds = [n * i // chunks for i in range(chunks + 1)]
     pipe.s_in.wait_stream(comp)
     pipe.s_out.wait_stream(comp)
+    pipe.acc.zero_()
     ready = []
     for lo, hi in zip(bounds, bounds[1:]):
         with torch.cuda.stream(pipe.s_in):
@@ -556,6 +668,7 @@ def map_cells_host(target_host: torch.Tensor, ref, ref_knn, k: int, metric: Opti
         comp.wait_event(ev)
         knn(pipe.dev_in[lo:hi], rd, k, met, dist_factor, ref_mask, False, 0, mode, out=(pipe.idx[lo:hi], pipe.dist[lo:hi]))
         snn_weights(pipe.idx[lo:hi], rk, k, out=(pipe.cnt[lo:hi], pipe.w[lo:hi]))
+        score_accumulate(pipe.idx[lo:hi], pipe.cnt[lo:hi], m, k, acc=pipe.acc)     # integer sums: piece order is immaterial
         done = torch.cuda.Event()
         done.record(comp)
         with torch.cuda.stream(pipe.s_out):
@@ -563,7 +676,7 @@ def map_cells_host(target_host: torch.Tensor, ref, ref_knn, k: int, metric: Opti
             pipe.host["idx"][lo:hi].copy_(pipe.idx[lo:hi], non_blocking=True)
             pipe.host["dist"][lo:hi].copy_(pipe.dist[lo:hi], non_blocking=True)
             pipe.host["weights"][lo:hi].copy_(pipe.w[lo:hi], non_blocking=True)
-    sc = mapping_scores(pipe.idx, pipe.cnt, m, k)
+    sc = scores_finalize(pipe.acc, n)
     pipe.host["scores"].copy_(sc, non_blocking=True)
     comp.synchronize()
     pipe.s_out.synchronize()

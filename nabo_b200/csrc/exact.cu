@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(NT, 1)
 knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ r, int ldr, int n_query,
                  int n_ref, int g, int k, double f, const uint8_t* __restrict__ mask, int drop_first,
                  int idx_offset, const int* __restrict__ row_ids, const int* __restrict__ n_rows_dev,
-                 int cap, int gc, const NaboExactSplit sp, int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+                 int cap, int gc, const NaboExactSplit sp, int32_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                 const NaboRoute route) {
     // gc = dimensions per shared-memory tile chunk (gc == g: the whole vectors, query tile loaded once; gc < g:
     // both tiles are streamed in chunks, the accumulators carry over - same sequential order of additions)
     extern __shared__ double smem[];
@@ -364,6 +365,9 @@ knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict
             continue;
         }
         const long long orow = row_ids ? row_ids[qi] : qi;
+        int32_t* oi;
+        double* od;
+        nabo_route_row(route, orow, k, out_idx, out_dist, oi, od);
         const int skip = drop_first ? 1 : 0;
         for (int t = lane; t < k; t += 32) {
             int src = t + skip;
@@ -379,8 +383,8 @@ knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict
                 }
                 id += idx_offset;
             }
-            out_idx[orow * k + t] = id;
-            out_dist[orow * k + t] = dv;
+            oi[t] = id;
+            od[t] = dv;
         }
     }
 }
@@ -396,7 +400,7 @@ static int exact_cap_for(int ksel) {
 __global__ void __launch_bounds__(128)
 fallback_merge_kernel(const NaboExactSplit sp, const int* __restrict__ row_ids, const int* __restrict__ n_rows_dev,
                       int k, int drop_first, int idx_offset, const uint8_t* __restrict__ mask, int capp,
-                      int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+                      int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const NaboRoute route) {
     extern __shared__ double smem[];
     const int n_rows = *n_rows_dev;
     if (n_rows > sp.f_max) return;
@@ -423,6 +427,9 @@ fallback_merge_kernel(const NaboExactSplit sp, const int* __restrict__ row_ids, 
     __syncwarp();
     warp_bitonic_sort(d, ix, capp, lane);
     const long long orow = row_ids[qi];
+    int32_t* oi;
+    double* od;
+    nabo_route_row(route, orow, k, out_idx, out_dist, oi, od);
     const int skip = drop_first ? 1 : 0;
     for (int t = lane; t < k; t += 32) {
         const int src = t + skip;
@@ -434,8 +441,8 @@ fallback_merge_kernel(const NaboExactSplit sp, const int* __restrict__ row_ids, 
             if (dv == CUDART_INF || (mask && mask[id])) dv = CUDART_NAN;
             id += idx_offset;
         }
-        out_idx[orow * k + t] = id;
-        out_dist[orow * k + t] = dv;
+        oi[t] = id;
+        od[t] = dv;
     }
 }
 
@@ -455,7 +462,7 @@ size_t nabo_exact_split_workspace(int ksel) {
 int nabo_knn_exact_fallback(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                             int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                             const int* row_ids, const int* n_rows_dev, void* split_ws, int32_t* out_idx,
-                            double* out_dist, cudaStream_t st) {
+                            double* out_dist, const NaboRoute& route, cudaStream_t st) {
     const int ksel = k + (drop_first ? 1 : 0);
     NaboExactSplit sp;
     sp.mode = 1;
@@ -464,34 +471,35 @@ int nabo_knn_exact_fallback(const double* q, int ldq, const double* r, int ldr, 
     sp.part_dist = (double*)split_ws;
     sp.part_idx = (int32_t*)(sp.part_dist + (size_t)sp.nsplit * sp.f_max * ksel);
     int rc = nabo_knn_exact_launch_ex(q, ldq, r, ldr, NABO_FALLBACK_SPLIT_ROWS, n_ref, g, ksel, metric, f, mask, 0, 0,
-                                      row_ids, n_rows_dev, sp, out_idx, out_dist, st);
+                                      row_ids, n_rows_dev, sp, out_idx, out_dist, route, st);
     if (rc) return rc;
     int capp = nabo_next_pow2(sp.nsplit * ksel);
     if (capp < 32) capp = 32;
     const size_t smem = (size_t)4 * capp * (sizeof(double) + sizeof(int));
     NABO_CUDA(cudaFuncSetAttribute(fallback_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fallback_merge_kernel<<<(NABO_FALLBACK_SPLIT_ROWS + 3) / 4, 128, smem, st>>>(sp, row_ids, n_rows_dev, k, drop_first,
-                                                                               idx_offset, mask, capp, out_idx, out_dist);
+                                                                               idx_offset, mask, capp, out_idx, out_dist,
+                                                                               route);
     NABO_LAUNCH_CHECK("fallback_merge_kernel");
     sp.mode = 2;
     return nabo_knn_exact_launch_ex(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
-                                    row_ids, n_rows_dev, sp, out_idx, out_dist, st);
+                                    row_ids, n_rows_dev, sp, out_idx, out_dist, route, st);
 }
 
 int nabo_knn_exact_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
                           int k, int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                           const int* row_ids, const int* n_rows_dev, int32_t* out_idx, double* out_dist,
-                          cudaStream_t st) {
+                          const NaboRoute& route, cudaStream_t st) {
     NaboExactSplit sp;
     sp.mode = 0; sp.nsplit = 1; sp.f_max = 0; sp.part_idx = nullptr; sp.part_dist = nullptr;
     return nabo_knn_exact_launch_ex(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
-                                    row_ids, n_rows_dev, sp, out_idx, out_dist, st);
+                                    row_ids, n_rows_dev, sp, out_idx, out_dist, route, st);
 }
 
 int nabo_knn_exact_launch_ex(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
                              int k, int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                              const int* row_ids, const int* n_rows_dev, const NaboExactSplit& sp, int32_t* out_idx,
-                             double* out_dist, cudaStream_t st) {
+                             double* out_dist, const NaboRoute& route, cudaStream_t st) {
     const int ksel = k + (drop_first ? 1 : 0);
     NABO_ARG(k >= 1 && ksel <= 128, "knn: k=%d unsupported (1 <= k, k + drop_first <= 128)", k);
     NABO_ARG(g >= 1, "knn: g=%d", g);
@@ -506,7 +514,7 @@ int nabo_knn_exact_launch_ex(const double* q, int ldq, const double* r, int ldr,
 #define LAUNCH(M)                                                                                         \
     NABO_CUDA(cudaFuncSetAttribute(knn_exact_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     knn_exact_kernel<M><<<grid, NT, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first, \
-                                                idx_offset, row_ids, n_rows_dev, cap, gc, sp, out_idx, out_dist);
+                                                idx_offset, row_ids, n_rows_dev, cap, gc, sp, out_idx, out_dist, route);
     if (metric == NABO_EUCLIDEAN) { LAUNCH(NABO_EUCLIDEAN) }
     else if (metric == NABO_MOD_CANBERRA) { LAUNCH(NABO_MOD_CANBERRA) }
     else if (metric == NABO_COSINE) { LAUNCH(NABO_COSINE) }
@@ -533,7 +541,7 @@ __device__ __forceinline__ double cert_lower_bound(const NaboCert& c, int qi, fl
     if (!(l2 > 0.0)) return 0.0;
     if (c.kind == NABO_CERT_EUCLID) {
         // |d~ - d| <= 2^-21 (|q| + |r|) from the two-term FP16 split of the inputs
-        return sqrt(l2) * sc_inv * (1.0 - 1e-7) - 9.6e-7 * (qn + rmax) * sc_inv;
+        return sqrt(l2) * sc_inv * (1.0 - 1e-7) - (9.6e-7 * (qn + rmax) + c.abs_slack) * sc_inv;
     }
     // cosine: unit vectors, chord e -> distance e^2 / 2
     double e = sqrt(l2) * sc_inv - 1.0e-6;
@@ -547,11 +555,14 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
               int n_ref, int g, int k, double f, const uint8_t* __restrict__ mask, int drop_first,
               int idx_offset, const int32_t* __restrict__ cand, int n_cand, int capp, const NaboCert cert,
               int* __restrict__ fail_rows, int* __restrict__ fail_count,
-              int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+              int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const NaboRoute route) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x * 4 + warp;
     if (qi >= n_query) return;
+    int32_t* oi;
+    double* od;
+    nabo_route_row(route, qi, k, out_idx, out_dist, oi, od);
     double* d = smem + (size_t)warp * capp;
     int* ix = (int*)(smem + (size_t)4 * capp) + (size_t)warp * capp;
     const double* x = q + (long long)qi * ldq;
@@ -595,8 +606,8 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
             if (dv == CUDART_INF) dv = CUDART_NAN;
             id += idx_offset;
         }
-        out_idx[(long long)qi * k + t] = id;
-        out_dist[(long long)qi * k + t] = dv;
+        oi[t] = id;
+        od[t] = dv;
     }
     if (cert.kind != NABO_CERT_NONE && lane == 0) {
         const float tau = cert.tau[qi];
@@ -611,7 +622,7 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
 int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                        const int32_t* cand, int n_cand, const NaboCert& cert, int* fail_rows, int* fail_count,
-                       int32_t* out_idx, double* out_dist, cudaStream_t st) {
+                       int32_t* out_idx, double* out_dist, const NaboRoute& route, cudaStream_t st) {
     NABO_ARG(n_cand >= 1 && n_cand <= 128, "rerank: n_cand=%d unsupported (1..128)", n_cand);
     NABO_ARG(k >= 1 && k + (drop_first ? 1 : 0) <= n_cand, "rerank: k=%d does not fit n_cand=%d", k, n_cand);
     if (n_query == 0) return 0;
@@ -622,7 +633,7 @@ int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n
 #define LAUNCH(M)                                                                                              \
     rerank_kernel<M><<<grid, 128, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first,       \
                                               idx_offset, cand, n_cand, capp, cert, fail_rows, fail_count,     \
-                                              out_idx, out_dist);
+                                              out_idx, out_dist, route);
     if (metric == NABO_EUCLIDEAN) { LAUNCH(NABO_EUCLIDEAN) }
     else if (metric == NABO_MOD_CANBERRA) { LAUNCH(NABO_MOD_CANBERRA) }
     else if (metric == NABO_COSINE) { LAUNCH(NABO_COSINE) }
@@ -639,8 +650,10 @@ extern "C" int nabo_rerank_exact(const double* q, int ldq, const double* r, int 
     NABO_ARG(q && r && cand && out_idx && out_dist, "rerank: null pointer");
     NABO_ARG(ldq >= g && ldr >= g, "rerank: leading dimension smaller than g");
     NaboCert none;
-    none.kind = NABO_CERT_NONE; none.tau = nullptr; none.qn2 = nullptr; none.scal = nullptr; none.c_acc = 0.0;
+    none.kind = NABO_CERT_NONE; none.tau = nullptr; none.qn2 = nullptr; none.scal = nullptr; none.c_acc = 0.0; none.abs_slack = 0.0;
+    NaboRoute plain;
+    plain.n_parts = 0;
     return nabo_rerank_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, dist_factor, ref_mask, drop_first,
-                              idx_offset, cand, n_cand, none, nullptr, nullptr, out_idx, out_dist,
+                              idx_offset, cand, n_cand, none, nullptr, nullptr, out_idx, out_dist, plain,
                               (cudaStream_t)stream);
 }

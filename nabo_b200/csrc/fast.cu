@@ -26,8 +26,8 @@ size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metri
 
 int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                   int metric, double f, const uint8_t* mask, int drop_first, int idx_offset, int32_t* out_idx,
-                  double* out_dist, void* workspace, size_t workspace_bytes, int64_t* stats_host,
-                  cudaStream_t st) {
+                  double* out_dist, const NaboRoute& route, void* workspace, size_t workspace_bytes,
+                  int64_t* stats_host, cudaStream_t st) {
     NaboStageTimer tm(stats_host != nullptr, st);
     tm.begin();
     const bool use_tc = (metric == NABO_EUCLIDEAN || metric == NABO_COSINE) && nabo_tc_supported(g, k, drop_first) &&
@@ -66,13 +66,13 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
         }
         tm.end(0);
         NaboCert cert;
-        cert.kind = NABO_CERT_LINEAR; cert.tau = tau; cert.qn2 = nullptr; cert.scal = nullptr; cert.c_acc = nabo_cb_eps(g);
+        cert.kind = NABO_CERT_LINEAR; cert.tau = tau; cert.qn2 = nullptr; cert.scal = nullptr; cert.c_acc = nabo_cb_eps(g); cert.abs_slack = 0.0;
         rc = nabo_rerank_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset, cand,
-                                kprime * n_split, cert, fail_rows, fail_count, out_idx, out_dist, st);
+                                kprime * n_split, cert, fail_rows, fail_count, out_idx, out_dist, route, st);
         if (rc) return rc;
         tm.end(1);
         rc = nabo_knn_exact_fallback(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
-                                     fail_rows, fail_count, split_ws, out_idx, out_dist, st);
+                                     fail_rows, fail_count, split_ws, out_idx, out_dist, route, st);
         if (rc) return rc;
         tm.end(2);
         if (stats_host) {
@@ -87,7 +87,7 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
     }
     if (!use_tc) {
         int rc = nabo_knn_exact_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
-                                       nullptr, nullptr, out_idx, out_dist, st);
+                                       nullptr, nullptr, out_idx, out_dist, route, st);
         tm.end(0);
         if (rc) return rc;
         if (stats_host) {
@@ -119,14 +119,15 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
     NaboCert cert;
     cert.kind = metric == NABO_COSINE ? NABO_CERT_COSINE : NABO_CERT_EUCLID;
     cert.tau = tau; cert.qn2 = qn2; cert.scal = scal; cert.c_acc = kCAcc;
+    cert.abs_slack = 2.0 * sqrt((double)g) * 5.9604644775390625e-08;
     rc = nabo_rerank_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset, cand,
-                            kprime * n_split, cert, fail_rows, fail_count, out_idx, out_dist, st);
+                            kprime * n_split, cert, fail_rows, fail_count, out_idx, out_dist, route, st);
     if (rc) return rc;
     tm.end(1);
     // rows the certificate did not clear: exact brute force (grid sized for the worst case,
     // blocks beyond the device-side row count exit immediately)
     rc = nabo_knn_exact_fallback(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
-                                 fail_rows, fail_count, split_ws, out_idx, out_dist, st);
+                                 fail_rows, fail_count, split_ws, out_idx, out_dist, route, st);
     if (rc) return rc;
     tm.end(2);
     if (stats_host) {

@@ -6,6 +6,8 @@
 //   nabo_merge_topk       (reference-sharded mode; result must equal the unsharded top-k)
 #include "common.cuh"
 
+#define NABO_MERGE_MAX_SHARDS 16
+
 // ------------------------------------------------------------------ SNN counts + weights
 // One warp per query.  A = the query's k neighbours, sorted once in shared memory plus a 256-bit
 // signature; one neighbour's own kNN row per iteration, lanes over its entries (one coalesced row read):
@@ -357,9 +359,17 @@ extern "C" int nabo_classify_targets(const int32_t* tgt_knn, const uint8_t* coun
 }
 
 // ------------------------------------------------------------------ shard merge
+// One warp per query: the k-lists of all shards (one (n_query x k) idx / dist block per shard, anywhere in
+// device-visible memory: slices of an all-gather result or the per-source blocks of an all-to-all / peer-written
+// receive buffer, consumed in place) are sorted by (distance, index) in shared memory.
+struct MergeParts {
+    const int32_t* idx[NABO_MERGE_MAX_SHARDS];
+    const double* dist[NABO_MERGE_MAX_SHARDS];
+};
+
 __global__ void __launch_bounds__(128)
-merge_kernel(const int32_t* __restrict__ idx, const double* __restrict__ dist, int n_shards, int n_query, int k,
-             int capp, int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+merge_kernel(const MergeParts parts, int n_shards, int n_query, int k, int capp, int drop_first,
+             int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x * 4 + warp;
@@ -372,11 +382,11 @@ merge_kernel(const int32_t* __restrict__ idx, const double* __restrict__ dist, i
         int id = 0x7fffffff;
         if (c < tot) {
             const int s = c / k, j = c - s * k;
-            const long long off = ((long long)s * n_query + qi) * k + j;
-            const int i0 = idx[off];
+            const long long off = (long long)qi * k + j;
+            const int i0 = parts.idx[s][off];
             if (i0 >= 0) {
                 id = i0;
-                dv = dist[off];
+                dv = parts.dist[s][off];
                 if (dv != dv) dv = CUDART_INF;
             }
         }
@@ -384,29 +394,113 @@ merge_kernel(const int32_t* __restrict__ idx, const double* __restrict__ dist, i
     }
     __syncwarp();
     warp_bitonic_sort(d, ix, capp, lane);
-    for (int t = lane; t < k; t += 32) {
-        int id = ix[t];
-        double dv = d[t];
+    const int ko = k - drop_first;                          // drop_first: the global "self" entry goes after the merge
+    for (int t = lane; t < ko; t += 32) {
+        int id = ix[t + drop_first];
+        double dv = d[t + drop_first];
         if (id == 0x7fffffff) { id = -1; dv = CUDART_NAN; }
         else if (dv == CUDART_INF) dv = CUDART_NAN;
-        out_idx[(long long)qi * k + t] = id;
-        out_dist[(long long)qi * k + t] = dv;
+        out_idx[(long long)qi * ko + t] = id;
+        out_dist[(long long)qi * ko + t] = dv;
     }
 }
 
-extern "C" int nabo_merge_topk(const int32_t* idx, const double* dist, int n_shards, int n_query, int k,
-                               int32_t* out_idx, double* out_dist, void* stream) {
-    NABO_ARG(n_shards >= 1 && k >= 1 && n_query >= 0, "merge: bad sizes");
-    NABO_ARG((long long)n_shards * k <= 2048, "merge: n_shards*k=%d exceeds 2048", n_shards * k);
-    if (n_query == 0) return 0;
-    NABO_ARG(idx && dist && out_idx && out_dist, "merge: null pointer");
+static int merge_launch(const MergeParts& parts, int n_shards, int n_query, int k, int drop_first, int32_t* out_idx,
+                        double* out_dist, cudaStream_t st) {
     int capp = nabo_next_pow2(n_shards * k);
     if (capp < 32) capp = 32;
     size_t smem = (size_t)4 * capp * (sizeof(double) + sizeof(int));
     NABO_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_kernel<<<(n_query + 3) / 4, 128, smem, (cudaStream_t)stream>>>(idx, dist, n_shards, n_query, k, capp,
-                                                                        out_idx, out_dist);
+    merge_kernel<<<(n_query + 3) / 4, 128, smem, st>>>(parts, n_shards, n_query, k, capp, drop_first ? 1 : 0, out_idx,
+                                                       out_dist);
     NABO_LAUNCH_CHECK("merge_kernel");
+    return 0;
+}
+
+extern "C" int nabo_merge_topk(const int32_t* idx, const double* dist, int n_shards, int n_query, int k,
+                               int32_t* out_idx, double* out_dist, void* stream) {
+    NABO_ARG(n_shards >= 1 && n_shards <= NABO_MERGE_MAX_SHARDS && k >= 1 && n_query >= 0, "merge: bad sizes");
+    NABO_ARG((long long)n_shards * k <= 2048, "merge: n_shards*k=%d exceeds 2048", n_shards * k);
+    if (n_query == 0) return 0;
+    NABO_ARG(idx && dist && out_idx && out_dist, "merge: null pointer");
+    MergeParts parts;
+    for (int s = 0; s < n_shards; ++s) {
+        parts.idx[s] = idx + (size_t)s * n_query * k;
+        parts.dist[s] = dist + (size_t)s * n_query * k;
+    }
+    return merge_launch(parts, n_shards, n_query, k, 0, out_idx, out_dist, (cudaStream_t)stream);
+}
+
+extern "C" int nabo_merge_topk_parts(int n_shards, const int32_t* const* shard_idx_host,
+                                     const double* const* shard_dist_host, int n_query, int k, int drop_first,
+                                     int32_t* out_idx, double* out_dist, void* stream) {
+    NABO_ARG(n_shards >= 1 && n_shards <= NABO_MERGE_MAX_SHARDS && k >= 1 && n_query >= 0, "merge_parts: bad sizes");
+    NABO_ARG((long long)n_shards * k <= 2048, "merge_parts: n_shards*k=%d exceeds 2048", n_shards * k);
+    NABO_ARG(!drop_first || k >= 2, "merge_parts: drop_first needs k >= 2");
+    if (n_query == 0) return 0;
+    NABO_ARG(shard_idx_host && shard_dist_host && out_idx && out_dist, "merge_parts: null pointer");
+    MergeParts parts;
+    for (int s = 0; s < n_shards; ++s) {
+        NABO_ARG(shard_idx_host[s] && shard_dist_host[s], "merge_parts: shard %d has no buffers", s);
+        parts.idx[s] = shard_idx_host[s];
+        parts.dist[s] = shard_dist_host[s];
+    }
+    return merge_launch(parts, n_shards, n_query, k, drop_first, out_idx, out_dist, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ GPU-count-independent mapping scores
+// Every SNN weight is one of k + 1 table values, so the sum over a reference cell's edges is an INTEGER
+// combination of them: acc[r] += iw[counts] with iw = the table in integer units (for the reference's table,
+// round(w, 2) in hundredths: exact).  Integer atomics commute, so acc - and with it the score - has the same
+// bits for any launch geometry, any order of target batches and any number of GPUs (acc is what the sharded
+// modes all-reduce, as int64).  nabo_mapping_scores (sorted, target order) stays the single-GPU default of the
+// Graph facade; the two agree to ~1e-15 relative (one rounding here, one per edge there).
+__global__ void __launch_bounds__(256)
+score_accumulate_kernel(const int32_t* __restrict__ tgt_knn, const uint8_t* __restrict__ counts,
+                        const long long* __restrict__ iw, long long n_edges, int k, int n_ref,
+                        const uint8_t* __restrict__ include, unsigned long long* __restrict__ acc) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_edges) return;
+    const int c = counts[e];
+    if (c == 0) return;
+    const int r = tgt_knn[e];
+    if (r < 0 || r >= n_ref) return;
+    if (include && !include[e / k]) return;
+    const long long w = iw[c];
+    if (w != 0) atomicAdd(acc + r, (unsigned long long)w);
+}
+
+__global__ void __launch_bounds__(256)
+score_finalize_kernel(const long long* __restrict__ acc, int n_ref, double unit, double mult, double denom,
+                      double min_score, double* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_ref) return;
+    const double sum = __ddiv_rn((double)acc[r], unit);           // exact integer / units per 1.0
+    const double v = __ddiv_rn(__dmul_rn(mult, sum), denom);
+    out[r] = v >= min_score ? v : 0.0;
+}
+
+extern "C" int nabo_score_accumulate(const int32_t* tgt_knn, const uint8_t* counts, const long long* int_weights,
+                                     int n_query, int k, int n_ref, const uint8_t* include, long long* acc,
+                                     void* stream) {
+    NABO_ARG(n_query >= 0 && k >= 1 && n_ref >= 1, "score_accumulate: bad sizes");
+    if (n_query == 0) return 0;
+    NABO_ARG(tgt_knn && counts && int_weights && acc, "score_accumulate: null pointer");
+    const long long e = (long long)n_query * k;
+    score_accumulate_kernel<<<(unsigned)((e + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        tgt_knn, counts, int_weights, e, k, n_ref, include, (unsigned long long*)acc);
+    NABO_LAUNCH_CHECK("score_accumulate_kernel");
+    return 0;
+}
+
+extern "C" int nabo_scores_finalize(const long long* acc, int n_ref, double units_per_one, double score_multiplier,
+                                    long long n_include, double min_score, double* out_scores, void* stream) {
+    NABO_ARG(n_ref >= 1 && units_per_one > 0.0 && n_include > 0, "scores_finalize: bad arguments");
+    NABO_ARG(acc && out_scores, "scores_finalize: null pointer");
+    score_finalize_kernel<<<(n_ref + 255) / 256, 256, 0, (cudaStream_t)stream>>>(acc, n_ref, units_per_one,
+                                                                               score_multiplier, (double)n_include,
+                                                                               min_score, out_scores);
+    NABO_LAUNCH_CHECK("score_finalize_kernel");
     return 0;
 }
 

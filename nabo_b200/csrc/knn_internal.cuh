@@ -2,6 +2,32 @@
 #pragma once
 #include "common.cuh"
 
+// Routed result rows (reference-sharded mode): result row t of a kNN call goes to part p with
+// bounds[p] <= t < bounds[p + 1], at row t - bounds[p] of that part's (rows x k) idx / dist blocks.  The blocks
+// may be anywhere the device can store to - slices of a local all-to-all send buffer, or the receive buffers of
+// the peer GPUs mapped over NVLink - so the kernel that produces a row also delivers it.  n_parts == 0: plain
+// contiguous out_idx / out_dist.
+#define NABO_MAX_PARTS 16
+struct NaboRoute {
+    int n_parts;
+    int bounds[NABO_MAX_PARTS + 1];
+    int32_t* idx[NABO_MAX_PARTS];
+    double* dist[NABO_MAX_PARTS];
+};
+__device__ __forceinline__ void nabo_route_row(const NaboRoute& rt, long long row, int k, int32_t* out_idx,
+                                               double* out_dist, int32_t*& ri, double*& rd) {
+    if (rt.n_parts == 0) {
+        ri = out_idx + row * k;
+        rd = out_dist + row * k;
+        return;
+    }
+    int p = 0;
+    while (p + 1 < rt.n_parts && row >= rt.bounds[p + 1]) ++p;
+    const long long local = row - rt.bounds[p];
+    ri = rt.idx[p] + local * k;
+    rd = rt.dist[p] + local * k;
+}
+
 // Split fallback: with at most NABO_FALLBACK_SPLIT_ROWS uncertified rows the exact engine splits the
 // reference range over blockIdx.y and merges the partial lists (a single block would otherwise scan
 // the whole reference alone and dominate the call).
@@ -17,16 +43,16 @@ size_t nabo_exact_split_workspace(int ksel);
 int nabo_knn_exact_launch_ex(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
                              int k, int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                              const int* row_ids, const int* n_rows_dev, const NaboExactSplit& sp, int32_t* out_idx,
-                             double* out_dist, cudaStream_t st);
+                             double* out_dist, const NaboRoute& route, cudaStream_t st);
 int nabo_knn_exact_fallback(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                             int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                             const int* row_ids, const int* n_rows_dev, void* split_ws, int32_t* out_idx,
-                            double* out_dist, cudaStream_t st);
+                            double* out_dist, const NaboRoute& route, cudaStream_t st);
 
 int nabo_knn_exact_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g,
                           int k, int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                           const int* row_ids, const int* n_rows_dev, int32_t* out_idx, double* out_dist,
-                          cudaStream_t st);
+                          const NaboRoute& route, cudaStream_t st);
 
 // Candidate certificate evaluated by the re-rank (see rerank_kernel).
 #define NABO_CERT_NONE 0
@@ -39,12 +65,14 @@ struct NaboCert {
     const double* qn2;     // [n_query] |q~|^2 in scaled units (Euclid / cosine)
     const double* scal;    // {sc, 1/sc, max scaled reference norm, cosine flag}
     double c_acc;          // accumulation-error constant (Euclid / cosine) or absolute slack (linear)
+    double abs_slack;      // Euclid: absolute split error in scaled units, 2 sqrt(g) 2^-24 (the FP16 low halves are
+                           // subnormal below |x| ~ 0.25, where the split error stops being relative)
 };
 
 int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                        const int32_t* cand, int n_cand, const NaboCert& cert, int* fail_rows, int* fail_count,
-                       int32_t* out_idx, double* out_dist, cudaStream_t st);
+                       int32_t* out_idx, double* out_dist, const NaboRoute& route, cudaStream_t st);
 
 struct NaboStageTimer;
 bool nabo_tc_supported(int g, int k, int drop_first);
@@ -80,8 +108,8 @@ int nabo_tau_min_launch(float* tau, int n_query, int n_split, cudaStream_t st);
 size_t nabo_fast_workspace_bytes(int n_query, int n_ref, int g, int k, int metric);
 int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                   int metric, double f, const uint8_t* mask, int drop_first, int idx_offset, int32_t* out_idx,
-                  double* out_dist, void* workspace, size_t workspace_bytes, int64_t* stats_host,
-                  cudaStream_t st);
+                  double* out_dist, const NaboRoute& route, void* workspace, size_t workspace_bytes,
+                  int64_t* stats_host, cudaStream_t st);
 
 // CUDA-event stage timer, active only when the caller asked for stats (stats_host != NULL).
 // Usage: begin(); <launch stage 0>; end(0); <launch stage 1>; end(1); ... sync; ns(i).

@@ -253,6 +253,18 @@ class Mapping:
         rnames, rknn = _rows_in_order(h5[self._refSortedDistGrp], self.refCells)
         tnames, tknn = _rows_in_order(h5[target_sorted_dist_grp], None)
         h5.close()
+        # calc_dist stores the k (+1) best entries of a row, not upstream's full argsort: a k raised after the
+        # distances were stored cannot be served from them (a narrower table is only legitimate when the
+        # reference itself has fewer cells than k)
+        m = len(self.refCells)
+        if tknn.shape[1] < k and tknn.shape[1] != m - (1 if target_name == self.refName else 0):
+            raise ValueError("ERROR: the stored distances of %r hold the %d nearest reference cells of each cell but "
+                             "k is now %d. Recompute them (use_stored_distances=False) with the current parameters."
+                             % (target_name, tknn.shape[1], k))
+        if rknn.shape[1] < k and rknn.shape[1] != m - 1:
+            raise ValueError("ERROR: the stored reference distances hold the %d nearest cells of each reference cell "
+                             "but k is now %d. Run make_ref_graph(use_stored_distances=False) with the current "
+                             "parameters first." % (rknn.shape[1], k))
         kk = min(k, tknn.shape[1])
         tk = np.ascontiguousarray(tknn[:, :kk], dtype=np.int32)
         rk = np.ascontiguousarray(rknn[:, :min(k, rknn.shape[1])], dtype=np.int32)

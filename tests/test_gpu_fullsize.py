@@ -38,6 +38,15 @@ def test_full_size_knn_properties(data, metric):
     rows = np.random.default_rng(0).choice(N, 768, replace=False)
     ei, ed = core.knn(tgt[torch.from_numpy(rows).cuda()].contiguous(), ref, K, metric, 0.25, mode="exact")
     assert np.array_equal(ei.cpu().numpy(), i[rows]) and np.array_equal(ed.cpu().numpy(), d[rows])
+    # ... and against the ORACLE (C port of the reference loops, independent of every kernel of this build) on 96
+    # of them: all 100 000 distances per row, full-row sort, first k
+    if metric != "cosine":                     # the reference has no cosine metric: the C port has none either
+        from oracle import c_port
+        c_port.build()
+        sub = rows[:96]
+        oi, od = c_port.knn(tgt[torch.from_numpy(sub).cuda()].cpu().numpy(), ref.cpu().numpy(), K, metric, 0.25,
+                            nthreads=4)
+        assert np.array_equal(oi, i[sub]) and np.array_equal(od, d[sub])
 
 
 def test_full_size_reference_sharding_and_scores(data):

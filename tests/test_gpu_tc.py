@@ -77,6 +77,28 @@ def test_fast_badly_scaled_inputs(core):
         assert st["rows_exact_fallback"] <= 8, (scale, st)
 
 
+def test_fast_outlier_query_shrinks_the_scale(core):
+    """One query ~400x larger than every reference norm fixes the power-of-two scale, so all other vectors land
+    below 0.25 in scaled units, where the FP16 low halves are subnormal and the split error is absolute, not
+    relative; the certificate carries an absolute slack term for that (fast.cu, cert.abs_slack).  Near-tie rows
+    must still come out exactly as the exact engine gives them."""
+    from nabo_b200 import synth
+    rng = np.random.default_rng(9)
+    r = synth.pc_mixture(6000, 50, seed=1) * 0.02
+    q = synth.pc_mixture(900, 50, seed=101) * 0.02
+    q[0] *= 400.0
+    # near ties around the k-th rank: pairs of references at almost the same distance from a query
+    for t in range(1, 60):
+        v = rng.normal(size=50)
+        v /= np.linalg.norm(v)
+        r[100 + 2 * t] = q[t] + 0.05 * v
+        r[101 + 2 * t] = q[t] - 0.05 * (1 + 3e-8) * v
+    for k in (1, 2, 12):
+        fi, fd, st = core.knn(q, r, k, "euclidean", mode="fast", return_stats=True)
+        ei, ed = core.knn(q, r, k, "euclidean", mode="exact")
+        assert same_bits(fd, ed) and np.array_equal(fi, ei), k
+
+
 def _split16(x):
     hi = x.astype(np.float16).astype(np.float64)
     lo = (x - hi).astype(np.float16).astype(np.float64)

@@ -14,7 +14,10 @@ from oracle import nabo_oracle as O
 
 
 class OracleEngine:
-    def knn(self, q, r, k, metric, f, ref_mask, drop_first, idx_offset, mode):
+    routed = False         # no device addresses on CPU: parallel.py copies the rows into the send blocks
+
+    def knn(self, q, r, k, metric, f, ref_mask, drop_first, idx_offset, mode, out_parts=None):
+        assert out_parts is None
         m = None if ref_mask is None else np.asarray(ref_mask)
         i, d = O.knn(q.numpy(), r.numpy(), k, metric, f, mask=m, drop_first=drop_first)
         return torch.from_numpy((i + idx_offset).astype(np.int32)), torch.from_numpy(d)
@@ -24,14 +27,26 @@ class OracleEngine:
         i = np.where(np.isnan(d) & (i < 0), -1, i)
         return torch.from_numpy(i.astype(np.int32)), torch.from_numpy(d)
 
+    def merge_parts(self, idx_blocks, dist_blocks, n_rows, k, drop_first):
+        i, d = self.merge_topk(torch.stack(idx_blocks), torch.stack(dist_blocks))
+        return (i[:, 1:].contiguous(), d[:, 1:].contiguous()) if drop_first else (i, d)
+
+    def score_accumulate(self, tgt_knn, counts, n_ref, k):
+        # integer weight sums per reference cell (hundredths; every SNN weight is round(w, 2))
+        iw = np.rint(O.snn_weight_lut(k) * 100).astype(np.int64)
+        acc = np.zeros(n_ref, dtype=np.int64)
+        t, c = tgt_knn.numpy().astype(np.int64), counts.numpy().astype(np.int64)
+        ok = (c > 0) & (t >= 0)
+        np.add.at(acc, t[ok], iw[c[ok]])
+        return torch.from_numpy(acc)
+
+    def scores_finalize(self, acc, n_total):
+        return torch.from_numpy(1000.0 * (acc.numpy().astype(np.float64) / 100.0) / n_total)
+
     def snn_weights(self, tgt_knn, ref_knn, k):
         c, w = O.snn_weights(tgt_knn.numpy().astype(np.int64), ref_knn.numpy().astype(np.int64), k)
         return torch.from_numpy(c), torch.from_numpy(w)
 
-    def mapping_scores(self, tgt_knn, counts, n_ref, k, n_total):
-        w = O.snn_weight_lut(k)[counts.numpy()]
-        s = O.mapping_scores(tgt_knn.numpy().astype(np.int64), w, n_ref, n_targets=n_total)
-        return torch.from_numpy(s)
 
 
 def _free_port():
@@ -67,6 +82,10 @@ def _worker(rank, world, port, out_dir):
     dist.all_gather_object(gathered, (qlo, qhi, ri.numpy(), rd.numpy()))
     ref_knn = np.concatenate([g[2] for g in sorted(gathered, key=lambda g: g[0])])
     ref_dst = np.concatenate([g[3] for g in sorted(gathered, key=lambda g: g[0])])
+    # the all-gathered form returns the same table on every rank
+    alo, ahi, ai, ad = P.knn_reference_sharded(rt, rt[lo:hi], lo, k, "euclidean", drop_first=True, engine=eng,
+                                               merge_slice=False)
+    assert (alo, ahi) == (0, len(ref)) and np.array_equal(ai.numpy(), ref_knn) and np.array_equal(ad.numpy(), ref_dst)
     rk = torch.from_numpy(ref_knn)
     # (a) target-sharded
     tlo, thi = P.shard_bounds(len(tgt), world, rank)
@@ -76,7 +95,7 @@ def _worker(rank, world, port, out_dir):
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), ref_knn=ref_knn, ref_dst=ref_dst, tlo=tlo, thi=thi,
              a_idx=a["idx"].numpy(), a_dist=a["dist"].numpy(), a_w=a["weights"].numpy(), a_sc=a["scores"].numpy(),
              b_lo=b["lo"], b_hi=b["hi"], b_idx=b["idx"].numpy(), b_dist=b["dist"].numpy(), b_w=b["weights"].numpy(),
-             b_sc=b["scores"].numpy())
+             b_sc=b["scores"].numpy(), a_acc=a["score_acc"].numpy(), b_acc=b["score_acc"].numpy())
     dist.destroy_process_group()
 
 
@@ -94,6 +113,8 @@ def test_sharded_modes_equal_single_process(tmp_path):
         assert np.array_equal(r["ref_knn"], ri) and np.array_equal(r["ref_dst"], rd)
         np.testing.assert_allclose(r["a_sc"], sc, rtol=1e-13)
         np.testing.assert_allclose(r["b_sc"], sc, rtol=1e-13)
+        # integer weight sums: identical in both modes and on both ranks, hence identical score bits
+        assert np.array_equal(r["a_acc"], res[0]["b_acc"]) and np.array_equal(r["a_sc"], res[0]["b_sc"])
     assert np.array_equal(np.concatenate([r["a_idx"] for r in res]), ti)
     assert np.array_equal(np.concatenate([r["a_dist"] for r in res]), td)
     assert np.array_equal(np.concatenate([r["a_w"] for r in res]), w)
