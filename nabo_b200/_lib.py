@@ -13,7 +13,7 @@ import re
 from typing import Dict, List
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnabo_b200.so")
+LIB_PATH = os.environ.get("NABO_B200_LIB") or os.path.join(HERE, "libnabo_b200.so")   # override: A/B builds (tools/)
 HEADER = os.path.join(os.path.dirname(HERE), "include", "nabo_b200.h")
 
 EUCLIDEAN, MOD_CANBERRA, COSINE = 0, 1, 2

@@ -28,6 +28,7 @@
 #include "select.cuh"
 
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace tc {
 
@@ -117,15 +118,17 @@ __global__ void scale_kernel(const unsigned int* __restrict__ maxq_bits, const u
 // One thread per row; 16-byte chunk kc of row r of tile t lands at
 //   t * TILE*kp*2 + kc * (TILE*16) + (r>>3)*128 + (r&7)*16
 // (core matrices of 8 rows x 16 B, K-chunk-major: SBO = 128 B, LBO = TILE*16 B).
+// perm (or NULL): packed row i holds input row perm[i] (locality order, see order_* below)
 template <bool IS_QUERY>
 __global__ void __launch_bounds__(TILE)
 pack_kernel(const double* __restrict__ x, int ld, int n, int g, int kp, const double* __restrict__ norms2,
-            const double* __restrict__ scal, const uint8_t* __restrict__ mask, __half* __restrict__ out,
-            double* __restrict__ qn2_out) {
+            const double* __restrict__ scal, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ perm,
+            __half* __restrict__ out, double* __restrict__ qn2_out) {
     const int r = threadIdx.x;
-    const long long row = (long long)blockIdx.x * TILE + r;
+    const long long prow = (long long)blockIdx.x * TILE + r;
     __half* tile = out + (size_t)blockIdx.x * TILE * kp;
-    const bool live = row < n;
+    const bool live = prow < n;
+    const long long row = live && perm ? (long long)perm[prow] : prow;
     const double sc = scal[0];
     const bool cosine = scal[3] != 0.0;
     double mul = sc;
@@ -178,6 +181,90 @@ pack_kernel(const double* __restrict__ x, int ld, int n, int g, int kp, const do
     if (IS_QUERY && live && qn2_out) qn2_out[row] = n2;
 }
 
+// ------------------------------------------------------------------ locality order
+// A query's threshold tau is only as tight as the best K' references it has met so far, and while it is loose
+// nearly every 32 x 32 warp chunk holds some score below some lane's tau and takes the append path.  Both
+// operands are therefore packed in LOCALITY ORDER - sorted by the nearest of N_CEN centroids (rows sampled from
+// the reference; leading min(g, 64) coordinates, FP32; one stable radix pass) - and every work item starts its
+// sweep at the reference tiles of its own queries' cluster: the neighbours arrive first, tau is final after a
+// few percent of the sweep, and the remaining tiles cost the no-hit path only.  All pairs are still evaluated on
+// the tensor cores; results do not change (the exact re-rank orders by (distance, index) of the ORIGINAL rows).
+constexpr int N_CEN = 64;
+constexpr int CEN_DIMS = 64;
+
+__global__ void centroid_gather_kernel(const double* __restrict__ r, int ld, int n_ref, int gs, int cosine,
+                                       float* __restrict__ cen) {
+    const int c = blockIdx.x, k = threadIdx.x;
+    const long long row = (long long)c * n_ref / N_CEN;
+    const double* p = r + row * ld;
+    __shared__ float inv;
+    if (k == 0) {
+        inv = 1.f;
+        if (cosine) {
+            double s = 0.0;
+            for (int i = 0; i < gs; ++i) s = fma(p[i], p[i], s);
+            inv = s > 0.0 ? (float)(1.0 / sqrt(s)) : 0.f;
+        }
+    }
+    __syncthreads();
+    if (k < gs) cen[c * CEN_DIMS + k] = (float)p[k] * inv;
+}
+
+__global__ void __launch_bounds__(256)
+cluster_assign_kernel(const double* __restrict__ x, int ld, int n, int gs, int cosine, const float* __restrict__ cen,
+                      uint32_t* __restrict__ cl, uint32_t* __restrict__ iota) {
+    __shared__ float sc[N_CEN * CEN_DIMS];
+    for (int i = threadIdx.x; i < N_CEN * CEN_DIMS; i += blockDim.x) sc[i] = cen[i];
+    __syncthreads();
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const double* p = x + (long long)row * ld;
+    float inv = 1.f;
+    if (cosine) {
+        float s = 0.f;
+        for (int k = 0; k < gs; ++k) { const float v = (float)p[k]; s = fmaf(v, v, s); }
+        inv = s > 0.f ? rsqrtf(s) : 0.f;
+    }
+    float acc[N_CEN];
+#pragma unroll
+    for (int c = 0; c < N_CEN; ++c) acc[c] = 0.f;
+    for (int k = 0; k < gs; ++k) {
+        const float v = (float)p[k] * inv;
+#pragma unroll
+        for (int c = 0; c < N_CEN; ++c) { const float d = v - sc[c * CEN_DIMS + k]; acc[c] = fmaf(d, d, acc[c]); }
+    }
+    int best = 0;
+    float bd = CUDART_INF_F;
+#pragma unroll
+    for (int c = 0; c < N_CEN; ++c)
+        if (acc[c] < bd) { bd = acc[c]; best = c; }            // NaN rows stay in cluster 0
+    cl[row] = (uint32_t)best;
+    iota[row] = (uint32_t)row;
+}
+
+// first[c] = first sorted position holding a cluster id >= c (c = 0 .. N_CEN)
+__global__ void cluster_first_kernel(const uint32_t* __restrict__ sorted_cl, int n, int* __restrict__ first) {
+    const int c = threadIdx.x;
+    if (c > N_CEN) return;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sorted_cl[mid] < (uint32_t)c) lo = mid + 1; else hi = mid;
+    }
+    first[c] = lo;
+}
+
+// start tile of every work item = where the cluster of its middle query begins in the sorted reference
+__global__ void item_start_kernel(const uint32_t* __restrict__ sorted_cl_q, int n_query, const int* __restrict__ first_r,
+                                  int n_items, int n_rtiles, int* __restrict__ start) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    long long mid = (long long)it * NQ * TILE + NQ * TILE / 2;
+    if (mid >= n_query) mid = n_query - 1;
+    int t = first_r[sorted_cl_q[mid]] / TILE;
+    start[it] = t < n_rtiles ? t : n_rtiles - 1;
+}
+
 // ------------------------------------------------------------------ the candidate kernel
 struct Params {
     const __half* qa;       // packed queries  [n_qtiles_padded][TILE*kp]
@@ -187,6 +274,9 @@ struct Params {
     unsigned long long* cand_buf;   // [gridDim][NQ*TILE][CAP]
     int32_t* cand_idx;      // [n_query][n_split][kc_out]
     float* cert_tau;        // [n_split][n_query]
+    const uint32_t* perm_q; // packed query row -> input row (NULL = identity)
+    const uint32_t* perm_r; // packed reference row -> input row (NULL = identity)
+    const int* item_start;  // first reference tile of every item's sweep (NULL = 0; unsplit kernel only)
     size_t a_off, b_off, sort_off, bar_off;
 };
 
@@ -198,6 +288,19 @@ struct Barriers {
 };
 
 using namespace sel;   // make_key, sort128, compact_sort(_inline), compact_select (select.cuh)
+
+#ifdef NABO_TC_STATS       // development counters (tools/probe_tc_stats.py): [0] warp chunks, [1] warp chunks with a hit,
+__device__ unsigned long long g_tc_stats[12];  // [2] lanes with a hit, [3] keys appended, [4] running compactions,
+                                               // cycles per warp: [5] compaction, [6] filter_chunk, [7] wait for the
+                                               // accumulator, [8] tcgen05.ld + wait, [9] final emit, [10] whole item loop
+#define TC_STAT(i, v) atomicAdd(&g_tc_stats[i], (unsigned long long)(v))
+#define TC_CLK(var) const long long var = clock64()
+#define TC_CLK_ADD(i, t0) do { if ((threadIdx.x & 31) == 0) TC_STAT(i, clock64() - (t0)); } while (0)
+#else
+#define TC_STAT(i, v)
+#define TC_CLK(var)
+#define TC_CLK_ADD(i, t0)
+#endif
 
 // 32 freshly loaded scores of one query: reduce with FMNMX3 and append the ones below tau
 __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid_cols, uint32_t col0, float tau,
@@ -218,6 +321,15 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid
         g4[gi] = ptx::min3(a, b, fminf(v[8 * gi + 6], v[8 * gi + 7]));
     }
     const float m = fminf(fminf(g4[0], g4[1]), fminf(g4[2], g4[3]));
+#ifdef NABO_TC_STATS
+    {
+        const unsigned hb = __ballot_sync(0xffffffffu, m < tau);
+        if ((threadIdx.x & 31) == 0) { TC_STAT(0, 1); if (hb) { TC_STAT(1, 1); TC_STAT(2, __popc(hb)); } }
+        int na = 0;
+        for (int i = 0; i < 32; ++i) na += v[i] < tau;
+        if (na) TC_STAT(3, na);
+    }
+#endif
     if (m < tau) {
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
@@ -235,16 +347,24 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid
 }
 
 // work item w -> (query item, first / last reference tile of its range)
+// The unsplit kernel sweeps all reference tiles cyclically from the item's start tile: sweep position jj in
+// [j0, j1) is tile sweep_tile(jj) (start = 0 and no wrap in the split kernel).
 template <bool SPLIT>
-__device__ __forceinline__ void decode_item(const Params& p, int w, int& qitem, int& seg, int& j0, int& j1) {
+__device__ __forceinline__ void decode_item(const Params& p, int w, int& qitem, int& seg, int& j0, int& j1, int& start) {
+    start = 0;
     if (!SPLIT) {                      // one piece: the instantiation the large-N path runs is the unsplit kernel
         qitem = w; seg = 0; j0 = 0; j1 = p.n_rtiles;
+        if (p.item_start) start = p.item_start[w];
         return;
     }
     qitem = w / p.n_split;
     seg = w - qitem * p.n_split;
     j0 = (int)((long long)p.n_rtiles * seg / p.n_split);
     j1 = (int)((long long)p.n_rtiles * (seg + 1) / p.n_split);
+}
+__device__ __forceinline__ int sweep_tile(int jj, int start, int n_rtiles) {
+    const int j = jj + start;
+    return j >= n_rtiles ? j - n_rtiles : j;
 }
 
 template <int KSTEPS, bool SPLIT>   // K steps of 16 known at compile time (0 = runtime loop); SPLIT: n_split > 1
@@ -276,8 +396,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         if (lane == 0) {
             uint32_t t = 0, it = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-                int item, seg, j0, j1;
-                decode_item<SPLIT>(p, w, item, seg, j0, j1);
+                int item, seg, j0, j1, start;
+                decode_item<SPLIT>(p, w, item, seg, j0, j1, start);
                 ptx::mbar_wait(&bars->a_empty, (it & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(&bars->a_full, NQ * a_tile_bytes);
                 for (int q = 0; q < NQ; ++q) {
@@ -290,7 +410,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                     const uint32_t s = t % p.stages, use = t / p.stages;
                     ptx::mbar_wait(&bars->b_empty[s], (use & 1) ^ 1);
                     ptx::mbar_arrive_expect_tx(&bars->b_full[s], a_tile_bytes);
-                    const char* src = reinterpret_cast<const char*>(p.rb) + (size_t)j * a_tile_bytes;
+                    const char* src = reinterpret_cast<const char*>(p.rb) + (size_t)sweep_tile(j, start, p.n_rtiles) * a_tile_bytes;
                     char* dst = reinterpret_cast<char*>(smem + p.b_off) + (size_t)s * a_tile_bytes;
                     for (uint32_t o = 0; o < a_tile_bytes; o += 8192)
                         ptx::bulk_g2s(dst + o, src + o, min(8192u, a_tile_bytes - o), &bars->b_full[s]);
@@ -313,8 +433,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
             const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off), lbo, sbo);
             uint32_t t = 0, it = 0, n = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-                int item, seg, j0, j1;
-                decode_item<SPLIT>(p, w, item, seg, j0, j1);
+                int item, seg, j0, j1, start;
+                decode_item<SPLIT>(p, w, item, seg, j0, j1, start);
                 ptx::mbar_wait(&bars->a_full, it & 1);
                 for (int j = j0; j < j1; ++j, ++t) {
                     const uint32_t s = t % p.stages, use = t / p.stages;
@@ -366,8 +486,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
             const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off), lbo, sbo);
             uint32_t t = 0, it = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-                int item, seg, j0, j1;
-                decode_item<SPLIT>(p, w, item, seg, j0, j1);
+                int item, seg, j0, j1, start;
+                decode_item<SPLIT>(p, w, item, seg, j0, j1, start);
                 ptx::mbar_wait(&bars->a_full, it & 1);
                 for (int j = j0; j < j1; ++j, ++t) {
                     const uint32_t s = t % p.stages, use = t / p.stages;
@@ -407,10 +527,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         uint32_t ks[4], kpl[4];
         uint32_t* hist = reinterpret_cast<uint32_t*>(smem + p.sort_off) + (size_t)warp * 256;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            int item, seg, j0, j1;
-            decode_item<SPLIT>(p, w, item, seg, j0, j1);
+            int item, seg, j0, j1, start;
+            decode_item<SPLIT>(p, w, item, seg, j0, j1, start);
+#ifdef NABO_TC_DBG_NOHIT
+            float tau = -CUDART_INF_F;              // timing experiment: nothing is ever appended (results invalid)
+#else
             float tau = CUDART_INF_F;
+#endif
             int cnt = 0;
+            TC_CLK(t_item);
             for (int j = j0; j < j1; ++j, ++t) {
 #if NABO_TC_ROTATE
                 const uint32_t job = t * NQ + q, buf = job & 3, acc_par = (job >> 2) & 1;
@@ -418,24 +543,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                 const uint32_t buf = q, acc_par = t & 1;
 #endif
                 const uint32_t taddr0 = tlane0 + buf * TILE;
+                TC_CLK(t_w);
                 ptx::mbar_wait(&bars->acc_full[buf], acc_par);
                 ptx::tc_fence_after();
-                const int col_limit = p.n_ref - j * TILE;        // columns >= col_limit are padding
+                TC_CLK_ADD(7, t_w);
+                const int jt = sweep_tile(j, start, p.n_rtiles);  // the reference tile this sweep position holds
+                const int col_limit = p.n_ref - jt * TILE;       // columns >= col_limit are padding
 #pragma unroll 1
                 for (int c = 0; c < TILE / CHUNK; ++c) {
                     uint32_t vr[32];
+                    TC_CLK(t_l);
                     ptx::tmem_ld_32x32(taddr0 + c * CHUNK, vr);
                     ptx::tmem_ld_wait();
+                    TC_CLK_ADD(8, t_l);
                     if (c == TILE / CHUNK - 1) {
                         // accumulator fully read: hand it back to the MMA warp before filtering
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[buf]);
                     }
-                    filter_chunk(vr, col_limit - c * CHUNK, (uint32_t)(j * TILE + c * CHUNK), tau, mybuf, cnt);
+                    TC_CLK(t_f);
+                    filter_chunk(vr, col_limit - c * CHUNK, (uint32_t)(jt * TILE + c * CHUNK), tau, mybuf, cnt);
+                    TC_CLK_ADD(6, t_f);
                     // hard limit: the next chunk may append 32 more; soft limit once per tile, after the release
                     const int lim = c == TILE / CHUNK - 1 ? p.soft : CAP - CHUNK;
                     unsigned need = __ballot_sync(0xffffffffu, cnt > lim);
+                    TC_CLK(t_c);
                     while (need) {
                         const int src = __ffs(need) - 1;
                         need &= need - 1;
@@ -445,11 +578,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                         int nc;
                         float nt;
                         compact_select(gb, n, lane, p.kprime, p.soft - 8, hist, nc, nt);
-                        if (lane == src) { cnt = nc; tau = nt; }
+                        if (lane == src) { cnt = nc; tau = nt; TC_STAT(4, 1); }
                     }
+                    TC_CLK_ADD(5, t_c);
                 }
             }
             // item done: final compaction of every query of this warp, emit candidates + threshold
+            TC_CLK(t_e);
             for (int src = 0; src < 32; ++src) {
                 unsigned long long* gb = reinterpret_cast<unsigned long long*>(
                     __shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
@@ -458,17 +593,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                 int nc;
                 float nt;
                 compact_sort_inline(gb, n, lane, p.kprime, ks, kpl, nc, nt);
-                const long long qg = (long long)item * NQ * TILE + q * TILE + quarter * 32 + src;
-                if (qg < p.n_query) {
+                const long long qp = (long long)item * NQ * TILE + q * TILE + quarter * 32 + src;   // packed position
+                if (qp < p.n_query) {
+                    const long long qg = p.perm_q ? (long long)p.perm_q[qp] : qp;                     // input row
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int i = u * 32 + lane;
-                        if (i < p.kc_out)
-                            p.cand_idx[(qg * n_seg + seg) * p.kc_out + i] = i < nc ? (int32_t)kpl[u] : -1;
+                        if (i < p.kc_out) {
+                            int32_t id = -1;
+                            if (i < nc) id = p.perm_r ? (int32_t)p.perm_r[kpl[u]] : (int32_t)kpl[u];
+                            p.cand_idx[(qg * n_seg + seg) * p.kc_out + i] = id;
+                        }
                     }
                     if (lane == 0) p.cert_tau[(long long)seg * p.n_query + qg] = n >= p.kprime ? nt : old_tau;
                 }
             }
+            TC_CLK_ADD(9, t_e);
+            TC_CLK_ADD(10, t_item);
         }
     }
     ptx::tc_fence_before();
@@ -495,6 +636,19 @@ int nabo_tc_kprime(int k, int drop_first) {
     int kprime = ksel + (ksel / 4 > 8 ? ksel / 4 : 8);
     if (kprime > tc::CAP - tc::CHUNK) kprime = tc::CAP - tc::CHUNK;
     return kprime;
+}
+
+// NABO_TC_ORDER=1 switches the locality order on.  Measured on B200 (tools/probe_tc_scan.py, probe_tc_stats.py):
+// it cuts the warp chunks that take the append path from 70 % to 8 % at 100 k x 100 k and the appends per query
+// from 506 to 373, but the kernel is bound by the TMEM read-out (64 B/clk/SM) plus the compactions, not by the
+// hit path, so the candidate pass gains 4 % there and the ten extra launches cost as much; off by default.
+static bool nabo_tc_order_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NABO_TC_ORDER");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
 }
 
 static int tc_grid(int n_items) {
@@ -545,6 +699,11 @@ size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_fi
     b += nabo_align_up((size_t)148 * tc::NQ * tc::TILE * tc::CAP * 8, 256);   // candidate buffers
     b += nabo_align_up((size_t)n_query * kprime * 4 * NABO_TC_MAX_SPLIT, 256);   // candidate indices (per reference range)
     b += nabo_align_up((size_t)n_query * 4 * NABO_TC_MAX_SPLIT, 256) + nabo_align_up((size_t)n_query * 4, 256);   // cert tau, fail rows
+    // locality order: cluster ids + row numbers (in / sorted) of both operands, radix scratch, centroids, tables
+    b += 4 * (nabo_align_up((size_t)n_query * 4, 256) + nabo_align_up((size_t)n_ref * 4, 256));
+    b += nabo_align_up(nabo_radix_pass_scratch_bytes(n_query > n_ref ? n_query : n_ref), 256);
+    b += nabo_align_up((size_t)tc::N_CEN * tc::CEN_DIMS * 4, 256) + nabo_align_up((size_t)(tc::N_CEN + 1) * 4, 256) +
+         nabo_align_up((size_t)n_items * 4, 256);
     b += 4096;
     return b;
 }
@@ -577,12 +736,46 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     unsigned int* maxbits = ar.take<unsigned int>(2);
     if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small for the tensor-core pass");
 
+    // locality order (see order kernels above): only worth its ~10 small launches on a real sweep
+    const bool ordered = n_split == 1 && n_rtiles >= 64 && nabo_tc_order_enabled();
+    uint32_t *perm_q = nullptr, *perm_r = nullptr;
+    int* item_start = nullptr;
+    if (ordered) {
+        uint32_t* cl_q = ar.take<uint32_t>(n_query);
+        uint32_t* io_q = ar.take<uint32_t>(n_query);
+        uint32_t* scl_q = ar.take<uint32_t>(n_query);
+        perm_q = ar.take<uint32_t>(n_query);
+        uint32_t* cl_r = ar.take<uint32_t>(n_ref);
+        uint32_t* io_r = ar.take<uint32_t>(n_ref);
+        uint32_t* scl_r = ar.take<uint32_t>(n_ref);
+        perm_r = ar.take<uint32_t>(n_ref);
+        char* rscratch = ar.take<char>(nabo_radix_pass_scratch_bytes(n_query > n_ref ? n_query : n_ref));
+        float* cen = ar.take<float>((size_t)tc::N_CEN * tc::CEN_DIMS);
+        int* first_r = ar.take<int>(tc::N_CEN + 1);
+        item_start = ar.take<int>(n_items);
+        if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small for the tensor-core pass");
+        const int gs = g < tc::CEN_DIMS ? g : tc::CEN_DIMS;
+        const int cosine = metric == NABO_COSINE ? 1 : 0;
+        tc::centroid_gather_kernel<<<tc::N_CEN, tc::CEN_DIMS, 0, st>>>(r, ldr, n_ref, gs, cosine, cen);
+        tc::cluster_assign_kernel<<<(n_query + 255) / 256, 256, 0, st>>>(q, ldq, n_query, gs, cosine, cen, cl_q, io_q);
+        tc::cluster_assign_kernel<<<(n_ref + 255) / 256, 256, 0, st>>>(r, ldr, n_ref, gs, cosine, cen, cl_r, io_r);
+        NABO_LAUNCH_CHECK("tc order kernels");
+        int rc = nabo_radix_pass_launch(cl_q, io_q, n_query, 0, rscratch, scl_q, perm_q, st);
+        if (rc) return rc;
+        rc = nabo_radix_pass_launch(cl_r, io_r, n_ref, 0, rscratch, scl_r, perm_r, st);
+        if (rc) return rc;
+        tc::cluster_first_kernel<<<1, 128, 0, st>>>(scl_r, n_ref, first_r);
+        tc::item_start_kernel<<<(n_items + 127) / 128, 128, 0, st>>>(scl_q, n_query, first_r, n_items, n_rtiles, item_start);
+        NABO_LAUNCH_CHECK("tc order kernels");
+        *launches += 11;
+    }
+
     NABO_CUDA(cudaMemsetAsync(maxbits, 0, 2 * sizeof(unsigned int), st));
     tc::norms_kernel<<<(n_query + 255) / 256, 256, 0, st>>>(q, ldq, n_query, g, qnorm, maxbits);
     tc::norms_kernel<<<(n_ref + 255) / 256, 256, 0, st>>>(r, ldr, n_ref, g, rnorm, maxbits + 1);
     tc::scale_kernel<<<1, 1, 0, st>>>(maxbits, maxbits + 1, metric == NABO_COSINE ? 1 : 0, scal);
-    tc::pack_kernel<true><<<n_qtiles, tc::TILE, 0, st>>>(q, ldq, n_query, g, kp, qnorm, scal, nullptr, qa, qn2);
-    tc::pack_kernel<false><<<n_rtiles, tc::TILE, 0, st>>>(r, ldr, n_ref, g, kp, rnorm, scal, mask, rb, nullptr);
+    tc::pack_kernel<true><<<n_qtiles, tc::TILE, 0, st>>>(q, ldq, n_query, g, kp, qnorm, scal, nullptr, perm_q, qa, qn2);
+    tc::pack_kernel<false><<<n_rtiles, tc::TILE, 0, st>>>(r, ldr, n_ref, g, kp, rnorm, scal, mask, perm_r, rb, nullptr);
     NABO_LAUNCH_CHECK("tc pack kernels");
     tm.end(3);
 
@@ -591,6 +784,7 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     p.n_query = n_query; p.n_ref = n_ref; p.kp = kp; p.n_items = n_items; p.n_rtiles = n_rtiles;
     p.stages = pl.stages; p.kprime = kprime; p.kc_out = kprime; p.n_split = n_split;
     p.cand_buf = cbuf; p.cand_idx = cand; p.cert_tau = tau;
+    p.perm_q = perm_q; p.perm_r = perm_r; p.item_start = item_start;
     p.a_off = pl.a_off; p.b_off = pl.b_off; p.sort_off = pl.sort_off; p.bar_off = pl.bar_off;
     p.soft = tc::CAP - tc::CHUNK - 16 > kprime ? tc::CAP - tc::CHUNK - 16 : kprime;
 #define NABO_TC_LAUNCH(KS)                                                                                          \
@@ -620,6 +814,15 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     *launches += 6;
     return 0;
 }
+
+#ifdef NABO_TC_STATS
+extern "C" int nabo_dbg_tc_stats(unsigned long long* out_host, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out_host, tc::g_tc_stats, sizeof(unsigned long long) * 12);
+    if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(tc::g_tc_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 // ------------------------------------------------------------------ public candidate-pass entry points
 extern "C" int nabo_knn_candidates_width(int k, int drop_first) { return nabo_tc_kprime(k, drop_first); }

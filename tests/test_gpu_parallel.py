@@ -146,6 +146,7 @@ def test_two_ranks_nccl(tmp_path, transport):
     # integer weight sums: the 2-rank scores have the bits of the 1-GPU integer path, in both sharded modes
     acc1 = core.score_accumulate(ti, cnt, len(ref), k)
     sc1 = core.scores_finalize(acc1, len(tgt))
+    acc1, sc1 = acc1.cpu().numpy(), np.asarray(sc1.cpu() if hasattr(sc1, "cpu") else sc1)
     for r in res:
         assert np.array_equal(r["a_acc"], acc1) and np.array_equal(r["b_acc"], acc1)
         assert np.array_equal(r["a_sc"], sc1) and np.array_equal(r["b_sc"], sc1)
