@@ -285,14 +285,22 @@ def merge_topk_parts(idx_ptrs, dist_ptrs, n_query: int, k: int, device, drop_fir
 
 
 # ----------------------------------------------------------------------------- (4) SNN weights
-def snn_weight_lut(k: int) -> np.ndarray:
+def snn_weight_lut(k: int, strict: bool = True) -> np.ndarray:
     """weight(snn) = round(snn / (2*(k-1) - snn), 2) with Python's round() on a double
-    (nabo/_mapping.py:185, 194).  Entry 0 = 0.0 (no edge, :195).  k=2 raises
-    ZeroDivisionError for snn=2 exactly as the reference does."""
+    (nabo/_mapping.py:185, 194).  Entry 0 = 0.0 (no edge, :195).
+
+    k = 2 has no weight for snn = 2 (division by zero).  Upstream raises ZeroDivisionError only when some
+    pair really shares both neighbours; ``strict=False`` fills that entry with NaN so that callers can raise
+    on an actual count of 2 (``Mapping.calc_snn`` does), ``strict=True`` raises as soon as the table is built."""
     factor = 2 * (k - 1)
     lut = np.zeros(k + 1, dtype=np.float64)
     for snn in range(1, k + 1):
-        lut[snn] = round(snn / (factor - snn), 2)
+        if factor == snn:
+            if strict:
+                raise ZeroDivisionError("division by zero")
+            lut[snn] = np.nan
+        else:
+            lut[snn] = round(snn / (factor - snn), 2)
     return lut
 
 
@@ -305,7 +313,7 @@ def _lut_dev(k: int, device) -> "torch.Tensor":
     key = (int(k), str(device))
     t = _LUT_DEV.get(key)
     if t is None:
-        t = _LUT_DEV[key] = torch.from_numpy(snn_weight_lut(k)).to(device)
+        t = _LUT_DEV[key] = torch.from_numpy(snn_weight_lut(k, strict=False)).to(device)
     return t
 
 
@@ -377,11 +385,11 @@ def snn_int_weights(k: int, min_weight: float = 0.0, weighted: bool = True) -> n
     """The SNN weight table in integer units for ``score_accumulate``: entry c = round(lut[c] * 100) (exact,
     every weight is ``round(x, 2)``, nabo/_mapping.py:185, 194), 0 where the edge does not count
     (c = 0, or weight <= min_weight, nabo/_graph.py:647-648); unweighted: 1 per counted edge (:649-650)."""
-    lut = snn_weight_lut(k)
+    lut = snn_weight_lut(k, strict=False)     # NaN (k = 2, snn = 2) never occurs in a stored graph
     iw = np.zeros(k + 1, dtype=np.int64)
     for c in range(1, k + 1):
         if weighted:
-            if lut[c] > min_weight:
+            if lut[c] > min_weight:                     # False for NaN
                 iw[c] = int(round(lut[c] * SCORE_UNITS))
                 if abs(iw[c] / SCORE_UNITS - lut[c]) > 1e-12:
                     raise ValueError("ERROR: weight table entry %r is not a multiple of 1/%d" % (lut[c], SCORE_UNITS))

@@ -45,6 +45,12 @@ constexpr int CHUNK = 32;           // columns per tcgen05.ld
 #ifndef NABO_TC_ROTATE
 #define NABO_TC_ROTATE 1
 #endif
+#ifndef NABO_TC_PIPE
+#define NABO_TC_PIPE 0
+#endif
+#ifndef NABO_TC_UNIFORM_HIT
+#define NABO_TC_UNIFORM_HIT 0
+#endif
 // accumulators in TMEM (128 columns each).  ROTATE: the NQ query tiles share NQ + 1 buffers in a fixed
 // rotation (job n = tile * NQ + q uses buffer n % 4), so the MMAs of a warpgroup's next tile run while it is
 // still reading the current one; otherwise one private buffer per query tile (MMA and epilogue alternate).
@@ -271,12 +277,15 @@ struct Params {
     const __half* rb;       // packed references [n_rtiles][TILE*kp]
     int n_query, n_ref, kp, n_items, n_rtiles, stages, kprime, kc_out, soft;
     int n_split;            // reference ranges per query item (work item = n_items x n_split, see nabo_tc_split)
-    unsigned long long* cand_buf;   // [gridDim][NQ*TILE][CAP]
-    int32_t* cand_idx;      // [n_query][n_split][kc_out]
-    float* cert_tau;        // [n_split][n_query]
+    unsigned long long* cand_buf;   // [work item][NQ*TILE][CAP]: every (query, reference range) owns CAP keys
+    int* cand_cnt;          // [work item][NQ*TILE] live keys of each buffer when its sweep ended
+    float* cand_tau;        // [work item][NQ*TILE] running threshold when its sweep ended
+    int32_t* cand_idx;      // [n_query][n_split][kc_out]      (written by emit_kernel)
+    float* cert_tau;        // [n_split][n_query]              (written by emit_kernel)
     const uint32_t* perm_q; // packed query row -> input row (NULL = identity)
     const uint32_t* perm_r; // packed reference row -> input row (NULL = identity)
     const int* item_start;  // first reference tile of every item's sweep (NULL = 0; unsplit kernel only)
+    int dbg;                // NABO_TC_DBG bit mask for timing experiments (0 in production): 1 = skip the final emit
     size_t a_off, b_off, sort_off, bar_off;
 };
 
@@ -293,18 +302,27 @@ using namespace sel;   // make_key, sort128, compact_sort(_inline), compact_sele
 __device__ unsigned long long g_tc_stats[12];  // [2] lanes with a hit, [3] keys appended, [4] running compactions,
                                                // cycles per warp: [5] compaction, [6] filter_chunk, [7] wait for the
                                                // accumulator, [8] tcgen05.ld + wait, [9] final emit, [10] whole item loop
-#define TC_STAT(i, v) atomicAdd(&g_tc_stats[i], (unsigned long long)(v))
+// accumulated in per-thread registers (tc_loc), flushed with one atomic per counter at the end of an item
+#define TC_STAT(i, v) (tc_loc[i] += (unsigned long long)(v))
 #define TC_CLK(var) const long long var = clock64()
-#define TC_CLK_ADD(i, t0) do { if ((threadIdx.x & 31) == 0) TC_STAT(i, clock64() - (t0)); } while (0)
+#define TC_CLK_ADD(i, t0) (tc_loc[i] += (unsigned long long)(clock64() - (t0)))
+#define TC_DECL unsigned long long tc_loc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define TC_FLUSH do { if ((threadIdx.x & 31) == 0) for (int i_ = 0; i_ < 12; ++i_) { if (tc_loc[i_]) atomicAdd(&g_tc_stats[i_], tc_loc[i_]); tc_loc[i_] = 0; } } while (0)
+#define TC_ARG , unsigned long long (&tc_loc)[12]
+#define TC_PASS , tc_loc
 #else
 #define TC_STAT(i, v)
 #define TC_CLK(var)
 #define TC_CLK_ADD(i, t0)
+#define TC_DECL
+#define TC_FLUSH
+#define TC_ARG
+#define TC_PASS
 #endif
 
 // 32 freshly loaded scores of one query: reduce with FMNMX3 and append the ones below tau
 __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid_cols, uint32_t col0, float tau,
-                                             unsigned long long* mybuf, int& cnt) {
+                                             unsigned long long* mybuf, int& cnt TC_ARG) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vr[i]);
@@ -327,9 +345,28 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid
         if ((threadIdx.x & 31) == 0) { TC_STAT(0, 1); if (hb) { TC_STAT(1, 1); TC_STAT(2, __popc(hb)); } }
         int na = 0;
         for (int i = 0; i < 32; ++i) na += v[i] < tau;
-        if (na) TC_STAT(3, na);
+        for (int o = 16; o > 0; o >>= 1) na += __shfl_xor_sync(0xffffffffu, na, o);
+        if ((threadIdx.x & 31) == 0) TC_STAT(3, na);
     }
 #endif
+#if NABO_TC_UNIFORM_HIT
+    // warp-uniform branches only (no divergence / reconvergence barriers): a group of 8 columns is appended with
+    // predicated stores whenever ANY lane holds a score below its threshold in it
+    if (__any_sync(0xffffffffu, m < tau)) {
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+            if (__any_sync(0xffffffffu, g4[gi] < tau)) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (v[8 * gi + i] < tau) {
+                        mybuf[cnt] = make_key(v[8 * gi + i], col0 + 8 * gi + i);
+                        ++cnt;
+                    }
+                }
+            }
+        }
+    }
+#else
     if (m < tau) {
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
@@ -344,6 +381,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid
             }
         }
     }
+#endif
 }
 
 // work item w -> (query item, first / last reference tile of its range)
@@ -521,14 +559,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         const int q = warp >> 2;                           // query tile of this warpgroup
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;
-        unsigned long long* mybuf = p.cand_buf + ((size_t)blockIdx.x * NQ * TILE + q * TILE + row) * CAP;
+        const int slot = q * TILE + row;                   // this thread's query inside a work item
         const uint32_t tlane0 = tmem_base + ((uint32_t)(quarter * 32) << 16);
         uint32_t t = 0;
-        uint32_t ks[4], kpl[4];
         uint32_t* hist = reinterpret_cast<uint32_t*>(smem + p.sort_off) + (size_t)warp * 256;
+        TC_DECL;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             int item, seg, j0, j1, start;
             decode_item<SPLIT>(p, w, item, seg, j0, j1, start);
+            unsigned long long* mybuf = p.cand_buf + ((size_t)w * NQ * TILE + slot) * CAP;
 #ifdef NABO_TC_DBG_NOHIT
             float tau = -CUDART_INF_F;              // timing experiment: nothing is ever appended (results invalid)
 #else
@@ -549,24 +588,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                 TC_CLK_ADD(7, t_w);
                 const int jt = sweep_tile(j, start, p.n_rtiles);  // the reference tile this sweep position holds
                 const int col_limit = p.n_ref - jt * TILE;       // columns >= col_limit are padding
-#pragma unroll 1
-                for (int c = 0; c < TILE / CHUNK; ++c) {
-                    uint32_t vr[32];
-                    TC_CLK(t_l);
-                    ptx::tmem_ld_32x32(taddr0 + c * CHUNK, vr);
-                    ptx::tmem_ld_wait();
-                    TC_CLK_ADD(8, t_l);
-                    if (c == TILE / CHUNK - 1) {
-                        // accumulator fully read: hand it back to the MMA warp before filtering
-                        ptx::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[buf]);
-                    }
-                    TC_CLK(t_f);
-                    filter_chunk(vr, col_limit - c * CHUNK, (uint32_t)(jt * TILE + c * CHUNK), tau, mybuf, cnt);
-                    TC_CLK_ADD(6, t_f);
-                    // hard limit: the next chunk may append 32 more; soft limit once per tile, after the release
-                    const int lim = c == TILE / CHUNK - 1 ? p.soft : CAP - CHUNK;
+                // the compaction of every lane whose buffer passed `lim` (soft limit once per tile, after the
+                // accumulator has been handed back; hard limit otherwise: the next chunk may append 32 more)
+                auto compact_over = [&](int lim) {
                     unsigned need = __ballot_sync(0xffffffffu, cnt > lim);
                     TC_CLK(t_c);
                     while (need) {
@@ -578,43 +602,93 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                         int nc;
                         float nt;
                         compact_select(gb, n, lane, p.kprime, p.soft - 8, hist, nc, nt);
-                        if (lane == src) { cnt = nc; tau = nt; TC_STAT(4, 1); }
+                        if (lane == src) { cnt = nc; tau = nt; }
+                        if (lane == 0) TC_STAT(4, 1);
                     }
                     TC_CLK_ADD(5, t_c);
+                };
+                auto release_acc = [&]() {      // accumulator fully read: hand it back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[buf]);
+                };
+#if NABO_TC_PIPE
+                // two register sets: the tcgen05.ld of the next chunk is in flight while the current one is filtered
+                uint32_t va[32], vb[32];
+                ptx::tmem_ld_32x32(taddr0, va);
+                ptx::tmem_ld_wait();
+#pragma unroll 1
+                for (int c = 0; c < TILE / CHUNK; c += 2) {
+                    ptx::tmem_ld_32x32(taddr0 + (c + 1) * CHUNK, vb);
+                    filter_chunk(va, col_limit - c * CHUNK, (uint32_t)(jt * TILE + c * CHUNK), tau, mybuf, cnt TC_PASS);
+                    compact_over(CAP - CHUNK);
+                    ptx::tmem_ld_wait();
+                    if (c + 2 < TILE / CHUNK) ptx::tmem_ld_32x32(taddr0 + (c + 2) * CHUNK, va);
+                    else release_acc();
+                    filter_chunk(vb, col_limit - (c + 1) * CHUNK, (uint32_t)(jt * TILE + (c + 1) * CHUNK), tau, mybuf, cnt TC_PASS);
+                    compact_over(c + 2 < TILE / CHUNK ? CAP - CHUNK : p.soft);
+                    if (c + 2 < TILE / CHUNK) ptx::tmem_ld_wait();
                 }
+#else
+#pragma unroll 1
+                for (int c = 0; c < TILE / CHUNK; ++c) {
+                    uint32_t vr[32];
+                    TC_CLK(t_l);
+                    ptx::tmem_ld_32x32(taddr0 + c * CHUNK, vr);
+                    ptx::tmem_ld_wait();
+                    TC_CLK_ADD(8, t_l);
+                    if (c == TILE / CHUNK - 1) release_acc();
+                    TC_CLK(t_f);
+                    filter_chunk(vr, col_limit - c * CHUNK, (uint32_t)(jt * TILE + c * CHUNK), tau, mybuf, cnt TC_PASS);
+                    TC_CLK_ADD(6, t_f);
+                    compact_over(c == TILE / CHUNK - 1 ? p.soft : CAP - CHUNK);
+                }
+#endif
             }
-            // item done: final compaction of every query of this warp, emit candidates + threshold
+            // item done: leave the buffer as it is; emit_kernel makes the final selection of every (query, range)
+            // at full occupancy instead of 32 serial sorts per warp here, with the tensor pipe idle meanwhile
             TC_CLK(t_e);
-            for (int src = 0; src < 32; ++src) {
-                unsigned long long* gb = reinterpret_cast<unsigned long long*>(
-                    __shfl_sync(0xffffffffu, (unsigned long long)mybuf, src));
-                const int n = __shfl_sync(0xffffffffu, cnt, src);
-                const float old_tau = __shfl_sync(0xffffffffu, tau, src);
-                int nc;
-                float nt;
-                compact_sort_inline(gb, n, lane, p.kprime, ks, kpl, nc, nt);
-                const long long qp = (long long)item * NQ * TILE + q * TILE + quarter * 32 + src;   // packed position
-                if (qp < p.n_query) {
-                    const long long qg = p.perm_q ? (long long)p.perm_q[qp] : qp;                     // input row
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = u * 32 + lane;
-                        if (i < p.kc_out) {
-                            int32_t id = -1;
-                            if (i < nc) id = p.perm_r ? (int32_t)p.perm_r[kpl[u]] : (int32_t)kpl[u];
-                            p.cand_idx[(qg * n_seg + seg) * p.kc_out + i] = id;
-                        }
-                    }
-                    if (lane == 0) p.cert_tau[(long long)seg * p.n_query + qg] = n >= p.kprime ? nt : old_tau;
-                }
-            }
+            p.cand_cnt[(size_t)w * NQ * TILE + slot] = cnt;
+            p.cand_tau[(size_t)w * NQ * TILE + slot] = tau;
             TC_CLK_ADD(9, t_e);
             TC_CLK_ADD(10, t_item);
+            TC_FLUSH;
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == TMEM_WARP) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// Final selection: one warp per (query, reference range).  Sorts the buffer the sweep left behind, emits the K'
+// best as reference rows of the INPUT order (perm_r) into the query's INPUT row (perm_q) and the threshold every
+// other reference of the range is at or above.
+__global__ void __launch_bounds__(256)
+emit_kernel(const Params p, int n_work, int n_seg) {
+    const int lane = threadIdx.x & 31;
+    const long long wq = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);          // (work item, slot)
+    if (wq >= (long long)n_work * NQ * TILE) return;
+    const int w = (int)(wq / (NQ * TILE)), slot = (int)(wq - (long long)w * NQ * TILE);
+    const int item = n_seg > 1 ? w / n_seg : w, seg = n_seg > 1 ? w - item * n_seg : 0;
+    const long long qp = (long long)item * NQ * TILE + slot;                       // packed position
+    if (qp >= p.n_query) return;
+    const int n = p.cand_cnt[wq];
+    const float old_tau = p.cand_tau[wq];
+    uint32_t ks[4], kpl[4];
+    int nc;
+    float nt;
+    compact_sort_inline(p.cand_buf + (size_t)wq * CAP, n, lane, p.kprime, ks, kpl, nc, nt);
+    const long long qg = p.perm_q ? (long long)p.perm_q[qp] : qp;                 // input row
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = u * 32 + lane;
+        if (i < p.kc_out) {
+            int32_t id = -1;
+            if (i < nc) id = p.perm_r ? (int32_t)p.perm_r[kpl[u]] : (int32_t)kpl[u];
+            p.cand_idx[(qg * n_seg + seg) * p.kc_out + i] = id;
+        }
+    }
+    if (lane == 0) p.cert_tau[(long long)seg * p.n_query + qg] = n >= p.kprime ? nt : old_tau;
 }
 
 }  // namespace tc
@@ -696,7 +770,7 @@ size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_fi
     b += nabo_align_up((size_t)n_rtiles * tb, 256);                   // packed references
     b += nabo_align_up((size_t)n_query * 8, 256) * 2;                 // q norms, qn2
     b += nabo_align_up((size_t)n_ref * 8, 256);                       // r norms
-    b += nabo_align_up((size_t)148 * tc::NQ * tc::TILE * tc::CAP * 8, 256);   // candidate buffers
+    b += nabo_align_up((size_t)n_items * NABO_TC_MAX_SPLIT * tc::NQ * tc::TILE * (tc::CAP * 8 + 8), 256) + 512;   // candidate buffers, counts, thresholds
     b += nabo_align_up((size_t)n_query * kprime * 4 * NABO_TC_MAX_SPLIT, 256);   // candidate indices (per reference range)
     b += nabo_align_up((size_t)n_query * 4 * NABO_TC_MAX_SPLIT, 256) + nabo_align_up((size_t)n_query * 4, 256);   // cert tau, fail rows
     // locality order: cluster ids + row numbers (in / sorted) of both operands, radix scratch, centroids, tables
@@ -729,7 +803,10 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     double* qnorm = ar.take<double>(n_query);
     double* qn2 = ar.take<double>(n_query);
     double* rnorm = ar.take<double>(n_ref);
-    unsigned long long* cbuf = ar.take<unsigned long long>((size_t)grid * tc::NQ * tc::TILE * tc::CAP);
+    const size_t n_slots = (size_t)n_items * n_split * tc::NQ * tc::TILE;
+    unsigned long long* cbuf = ar.take<unsigned long long>(n_slots * tc::CAP);
+    int* ccnt = ar.take<int>(n_slots);
+    float* ctau = ar.take<float>(n_slots);
     int32_t* cand = ar.take<int32_t>((size_t)n_query * kprime * n_split);
     float* tau = ar.take<float>((size_t)n_query * n_split);
     double* scal = ar.take<double>(4);
@@ -783,8 +860,12 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     p.qa = qa; p.rb = rb;
     p.n_query = n_query; p.n_ref = n_ref; p.kp = kp; p.n_items = n_items; p.n_rtiles = n_rtiles;
     p.stages = pl.stages; p.kprime = kprime; p.kc_out = kprime; p.n_split = n_split;
-    p.cand_buf = cbuf; p.cand_idx = cand; p.cert_tau = tau;
+    p.cand_buf = cbuf; p.cand_cnt = ccnt; p.cand_tau = ctau; p.cand_idx = cand; p.cert_tau = tau;
     p.perm_q = perm_q; p.perm_r = perm_r; p.item_start = item_start;
+    {
+        const char* e = getenv("NABO_TC_DBG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     p.a_off = pl.a_off; p.b_off = pl.b_off; p.sort_off = pl.sort_off; p.bar_off = pl.bar_off;
     p.soft = tc::CAP - tc::CHUNK - 16 > kprime ? tc::CAP - tc::CHUNK - 16 : kprime;
 #define NABO_TC_LAUNCH(KS)                                                                                          \
@@ -804,12 +885,15 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     else NABO_TC_LAUNCH(0);
 #undef NABO_TC_LAUNCH
     NABO_LAUNCH_CHECK("candidates_kernel");
+    tm.end(0);             // the final selection below is timed with the re-rank stage
+    tc::emit_kernel<<<(unsigned)((n_slots + 7) / 8), 256, 0, st>>>(p, n_items * n_split, n_split);
+    NABO_LAUNCH_CHECK("emit_kernel");
+    *launches += 1;
     if (n_split > 1) {
         int rc = nabo_tau_min_launch(tau, n_query, n_split, st);
         if (rc) return rc;
         *launches += 1;
     }
-    tm.end(0);
     *cand_idx_out = cand; *kprime_out = kprime; *cert_tau_out = tau; *qn2_out = qn2; *scal_out = scal;
     *launches += 6;
     return 0;

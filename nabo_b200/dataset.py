@@ -318,10 +318,19 @@ class Dataset:
         keep = np.asarray(self.keepCellsIdx)
         ip, ix, vl = self._counts_csr()
         pos = np.full(self.rawNGenes, -1, dtype=np.int32)
-        pos[goi[goi >= 0]] = np.nonzero(goi >= 0)[0].astype(np.int32)
+        present = goi[goi >= 0]
+        pos[present] = np.nonzero(goi >= 0)[0].astype(np.int32)
         out = np.empty((len(keep), comps.shape[0]), dtype=np.float64)
-        for s in range(0, len(keep), chunk):
-            rows = keep[s:s + chunk]
+        # a gene listed twice in scaling_params has ONE column in the dataset but two model positions (upstream's
+        # a[goi] copies it to both, _dataset.py:905-911); the CSR kernel's gene -> position map holds one position
+        # per gene, so such a model goes through the dense gather, which takes any goi
+        duplicated = len(np.unique(present)) != len(present)
+        for s in range(0, len(keep), chunk if not duplicated else min(chunk, 4096)):
+            rows = keep[s:s + (chunk if not duplicated else min(chunk, 4096))]
+            if duplicated:
+                out[s:s + len(rows)] = core.project(self._dense(rows), goi, self.sf[rows].astype(np.float32), mu, sigma,
+                                                    comps, mean)
+                continue
             lens = ip[rows + 1] - ip[rows]
             sub_ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
             take = np.concatenate([np.arange(ip[r], ip[r + 1]) for r in rows]) if len(rows) else np.zeros(0, np.int64)

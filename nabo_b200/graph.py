@@ -142,7 +142,7 @@ class Graph(nx.Graph):
         k = int(g["k"][0])
         ref_suffix = g["ref_suffix"][0].decode("UTF-8") if "ref_suffix" in g else (self.refName or name)
         self._samples[name] = _Sample(nodes, knn, snn, k)
-        lut = core.snn_weight_lut(k)
+        lut = core.snn_weight_lut(k, strict=False)
         rows, cols = np.nonzero(snn > 0)
         nb = knn[rows, cols]
         w = lut[snn[rows, cols]]

@@ -268,8 +268,9 @@ class Mapping:
         kk = min(k, tknn.shape[1])
         tk = np.ascontiguousarray(tknn[:, :kk], dtype=np.int32)
         rk = np.ascontiguousarray(rknn[:, :min(k, rknn.shape[1])], dtype=np.int32)
-        core.snn_weight_lut(k)                              # k=2 raises ZeroDivisionError as upstream (:194)
         cnt, _ = core.snn_weights(tk, rk, kk) if kk == k else _snn_with_k(tk, rk, k)
+        if 2 * (k - 1) <= k and int(np.asarray(cnt).max(initial=0)) == 2 * (k - 1):
+            raise ZeroDivisionError("division by zero")     # snn == 2 (k - 1): upstream's weight divides by zero (:194)
         fix_edges = np.zeros((0, 2), dtype=np.int64)
         fw = None
         if target_name == self.refName:
@@ -403,7 +404,7 @@ def _write_reference_layout(g, tnames, target_name, rnames, ref_name, knn, cnt, 
     the weight is stored as its decimal string, exactly like upstream.  For the reference graph (undirected,
     targets = reference cells) a node lists every incident edge, with the weight of the LAST add_edge for that
     pair (:196-198) and the repair edges."""
-    lut = core.snn_weight_lut(k)
+    lut = core.snn_weight_lut(k, strict=False)
     rows, cols = np.nonzero(cnt > 0)
     nb = knn[rows, cols].astype(np.int64)
     w = lut[cnt[rows, cols]]
@@ -450,4 +451,4 @@ def _rows_in_order(grp, order: Optional[List[str]]):
 def _snn_with_k(tk: np.ndarray, rk: np.ndarray, k: int):
     """Stored rows shorter than k (fewer reference cells than k): counts with the weight table of k."""
     cnt, _ = core.snn_weights(tk, rk, tk.shape[1])
-    return cnt, core.snn_weight_lut(k)[cnt]
+    return cnt, core.snn_weight_lut(k, strict=False)[cnt]

@@ -48,9 +48,10 @@ def set_memory_only(flag: bool) -> None:
 class Dataset:
     """A named array.  Mirrors the slice of ``h5py.Dataset`` the path uses."""
 
-    def __init__(self, data, name: str = ""):
+    def __init__(self, data, name: str = "", parent: Optional["Group"] = None):
         self._a = data if isinstance(data, np.ndarray) else np.asarray(data)
         self.name = name
+        self._parent = parent          # the group holding it: its _root is the file to mark dirty on writes
 
     # -- numpy-ish protocol
     @property
@@ -80,7 +81,13 @@ class Dataset:
         return self._a[key]
 
     def __setitem__(self, key, value):
+        """In-place write (``h5['g/x'][i] = v``): refused on a file opened 'r', persisted by the next flush."""
+        root = self._parent._root if self._parent is not None else None
+        if root is not None and getattr(root, "mode", "a") == "r":
+            raise OSError("Can't write data (file %r was opened read-only)" % getattr(root, "filename", ""))
         self._a[key] = value
+        if root is not None:
+            root._dirty = True
 
     def __repr__(self):
         return "<store.Dataset %r shape %s dtype %s>" % (self.name, self.shape, self.dtype)
@@ -185,7 +192,7 @@ class Group:
                 arr = np.char.encode(arr, "utf-8")
             if shape is not None and tuple(np.atleast_1d(shape)) != arr.shape:
                 arr = arr.reshape(shape)
-        ds = Dataset(arr, node.name.rstrip("/") + "/" + leaf)
+        ds = Dataset(arr, node.name.rstrip("/") + "/" + leaf, node)
         node._c[leaf] = ds
         self._touch()
         return ds
@@ -239,7 +246,7 @@ class RowGroup(Group):
             return k in self.o._idx()
 
         def __getitem__(self, k):
-            return Dataset(self.o.data[self.o._idx()[k]], self.o.name + "/" + k)
+            return Dataset(self.o.data[self.o._idx()[k]], self.o.name + "/" + k, self.o)
 
         def keys(self):
             return self.o._idx().keys()
@@ -275,6 +282,14 @@ class RowGroup(Group):
 # (mtime_ns, size) is unchanged: the facade opens the same mapping file once per step (as the reference does
 # with h5py), and re-parsing a container of (cells x k) tables each time would dominate a 20 ms GPU job.
 _CONTENT_CACHE: Dict[str, tuple] = {}
+_CONTENT_CACHE_MAX = 8          # files; least recently stored goes first
+
+
+def _cache_put(key: str, value: tuple) -> None:
+    _CONTENT_CACHE.pop(key, None)
+    _CONTENT_CACHE[key] = value
+    while len(_CONTENT_CACHE) > _CONTENT_CACHE_MAX:
+        _CONTENT_CACHE.pop(next(iter(_CONTENT_CACHE)))
 
 
 def _stat_key(fn: str):
@@ -373,7 +388,7 @@ class File(Group):
                 names = np.load(io.BytesIO(z.read(nkey)), allow_pickle=False)
                 data = np.load(io.BytesIO(z.read(dkey)), allow_pickle=False)
                 Group.create_row_group(self, path, list(names), data)._names_enc = names
-        _CONTENT_CACHE[key] = (_stat_key(self.filename), self._c)
+        _cache_put(key, (_stat_key(self.filename), self._c))
         self._dirty = False
 
     def _persist(self):
@@ -417,7 +432,7 @@ class File(Group):
             rec(self, "")
             z.writestr("__manifest__.json", json.dumps(manifest))
         os.replace(tmp, self.filename)
-        _CONTENT_CACHE[os.path.abspath(self.filename)] = (_stat_key(self.filename), self._c)
+        _cache_put(os.path.abspath(self.filename), (_stat_key(self.filename), self._c))
         self._dirty = False
 
     def flush(self):

@@ -194,3 +194,48 @@ def test_batched_writes_defer_and_replay(tmp_path):
         with store.File(fn, "r") as h:
             assert "a" in h
     assert os.stat(fn).st_mtime_ns == stamp
+
+
+def test_in_place_dataset_writes_persist_and_read_only_files_refuse_them(tmp_path):
+    """h5['g/x'][i] = v on a file opened 'a' / 'r+' reaches the disk at the next flush (h5py behaviour); the same on a
+    file opened 'r' raises instead of leaking into the content cache."""
+    from nabo_b200 import store
+    fn = str(tmp_path / "w.h5")
+    h = store.File(fn, "w")
+    h.create_group("g").create_dataset("x", data=np.zeros(4))
+    h.create_row_group("rows", ["a", "b"], np.zeros((2, 3)))
+    h.close()
+    h = store.File(fn, "r+")
+    h["g/x"][1] = 5.0
+    h["rows"]["b"][2] = 7.0
+    h.close()
+    store._CONTENT_CACHE.clear()                     # force a real read of the container
+    h = store.File(fn, "r")
+    assert h["g/x"][:].tolist() == [0.0, 5.0, 0.0, 0.0] and h["rows"]["b"][:].tolist() == [0.0, 0.0, 7.0]
+    with pytest.raises(OSError, match="read-only"):
+        h["g/x"][0] = 1.0
+    with pytest.raises(OSError, match="read-only"):
+        h["rows"]["a"][0] = 1.0
+    h.close()
+    assert store.File(fn, "r")["g/x"][0] == 0.0
+
+
+def test_content_cache_is_bounded(tmp_path):
+    from nabo_b200 import store
+    store._CONTENT_CACHE.clear()
+    for i in range(store._CONTENT_CACHE_MAX + 5):
+        h = store.File(str(tmp_path / ("f%d.h5" % i)), "w")
+        h.create_dataset("x", data=np.arange(3))
+        h.close()
+    assert len(store._CONTENT_CACHE) <= store._CONTENT_CACHE_MAX
+
+
+def test_weight_table_for_k2_is_lazy():
+    """k = 2: upstream divides by zero only if a pair really shares both neighbours (nabo/_mapping.py:194)."""
+    from nabo_b200 import core
+    lut = core.snn_weight_lut(2, strict=False)
+    assert lut[0] == 0.0 and lut[1] == 1.0 and np.isnan(lut[2])
+    with pytest.raises(ZeroDivisionError):
+        core.snn_weight_lut(2)
+    assert core.snn_int_weights(2).tolist() == [0, 100, 0]
+    assert core.snn_weight_lut(1).tolist() == [0.0, -1.0]

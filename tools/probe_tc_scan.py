@@ -5,7 +5,7 @@ import torch
 sys.path.insert(0, ".")
 from nabo_b200 import core, synth
 
-g, k = 50, 30
+g, k = 50, int(os.environ.get("PROBE_K", "30"))
 shapes = [(100000, 100000), (56832, 100000), (100000, 200000), (100000, 400000), (56832, 1250000)]
 if len(sys.argv) > 1:
     shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
@@ -23,6 +23,6 @@ for n, m in shapes:
     ms = a.elapsed_time(b) / 3
     waves = -(-(-(-n // 384)) // 148)
     jobs = waves * 3 * -(-m // 128)
-    print("%s order=%s  %7d x %7d: %.3f ms  %.3e pairs/s  %.3f us per (128x128) job on the critical SM" % (
-        os.path.basename(os.environ.get("NABO_B200_LIB", "product")), os.environ.get("NABO_TC_ORDER", "1"), n, m, ms,
+    print("k=%d %s order=%s  %7d x %7d: %.3f ms  %.3e pairs/s  %.3f us per (128x128) job on the critical SM" % (
+        k, os.path.basename(os.environ.get("NABO_B200_LIB", "product")), os.environ.get("NABO_TC_ORDER", "1"), n, m, ms,
         n * m / ms * 1e3, ms * 1e3 / jobs))
