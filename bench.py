@@ -54,6 +54,7 @@ def parse():
                          "reference, all GPUs map the same --n-query targets, candidates are all-gathered and merged "
                          "(BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-projection", action="store_true", help="skip the projection (A1/A2) measurement")
     ap.add_argument("--no-ref-sharded", action="store_true", help="skip the reference-sharded (config 4) block")
     ap.add_argument("--ref-rows-per-gpu", type=int, default=1_250_000)
     ap.add_argument("--ref-batch", type=int, default=200_000, help="targets per step of the reference-sharded block")
@@ -371,6 +372,53 @@ def ref_sharded_block(a, dev, rank, world, rows_per_gpu, n_batch, n_batches, ste
     return block
 
 
+def projection_block(dev, steps=5, warmup=2, shapes=None):
+    """A1/A2 of the path (get_scaled_values + transform_pca, nabo/_dataset.py:905-913, 1028) on dense count blocks
+    of the BASELINE shapes: config 1 (5 000 cells, 2 000 HVGs -> 25 PCs) and a config-5 sample slice (262 144 of
+    the 500 000 cells, 2 000 HVGs -> 50 PCs; the kernel is linear in cells).  Algorithmic work:
+    2*G*C flop per cell, 4*G bytes of counts per cell in, 8*C out.  Both engines are timed: the FP64 tensor-core
+    GEMM (nabo_project_dense_mma, the product path) and the simple FP64 CUDA-core kernel it replaced."""
+    import torch
+    from nabo_b200 import core, synth
+    out = {}
+    fp64_peak = 40.0        # TFLOP/s, NVIDIA's B200 FP64 figure (no measured FP64 peak in MEASURED_PEAKS.json)
+    peaks = load_peaks()
+    for name, n, G, nc in (shapes or (("config1", 5000, 2000, 25), ("config5_slice", 262144, 2000, 50))):
+        counts = synth.nb_counts_device(n, G, seed=11, device=dev)
+        tot = counts.sum(1)
+        sf = (1000.0 / torch.where(tot > 0, tot, torch.ones_like(tot))).to(torch.float32)
+        x = counts[:4096] * sf[:4096, None]
+        mu = x.mean(0).to(torch.float64)
+        sigma = x.std(0).to(torch.float64) + 1e-3
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(5)
+        comps = torch.linalg.qr(torch.randn((G, nc), generator=gen, device=dev, dtype=torch.float64))[0].T.contiguous()
+        mean = 0.1 * torch.randn(G, generator=gen, device=dev, dtype=torch.float64)
+        gi = torch.arange(G, dtype=torch.int32, device=dev)
+        res = torch.empty((n, nc), dtype=torch.float64, device=dev)
+        entry = {"cells": n, "genes": G, "comps": nc, "nonzero_fraction": float((counts > 0).float().mean())}
+        for engine in ("mma", "simple"):
+            for _ in range(warmup):
+                core.project(counts, gi, sf, mu, sigma, comps, mean, engine=engine, out=res)
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for s_, e_ in ev:
+                s_.record()
+                core.project(counts, gi, sf, mu, sigma, comps, mean, engine=engine, out=res)
+                e_.record()
+            torch.cuda.synchronize()
+            ms = sum(_ev_ms(ev)) / steps
+            flops, nbytes = 2.0 * G * nc * n, 4.0 * n * G + 8.0 * n * nc
+            entry[engine] = {"ms": ms, "cells_per_s": n / (ms / 1e3), "fp64_tflops": flops / (ms * 1e-3) / 1e12,
+                             "frac_fp64_peak": flops / (ms * 1e-3) / 1e12 / fp64_peak, "gb_per_s": nbytes / (ms * 1e-3) / 1e9,
+                             "frac_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        entry["bound"] = "fp64 pipe (nominal %.0f TFLOP/s); the counts (4*G B per cell) stream once from HBM" % fp64_peak
+        out[name] = entry
+        del counts, res
+    torch.cuda.empty_cache()
+    return out
+
+
 def score_determinism_check(dev, rank, world, ref, ref_knn, k, n_targets=65_536):
     """The same fixed problem (n_targets targets, the config-2 reference) mapped three ways - unsharded on one
     GPU, target-sharded and reference-sharded over all ranks - must give the SAME per-reference score bits: the
@@ -583,6 +631,10 @@ def run_b200(a):
         line["ref_sharded"] = ref_sharded_block(a, dev, rank, world, a.ref_rows_per_gpu, a.ref_batch, 5,
                                                 max(5, a.steps // 2), 2)
         line["score_determinism"] = score_determinism_check(dev, rank, world, ref, ref_knn, k)
+    if rank == 0 and not a.no_projection:
+        line["projection"] = projection_block(dev)
+    if world > 1:
+        dist.barrier()
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline and a.metric != "cosine":
         threads = os.cpu_count() or 1

@@ -224,6 +224,14 @@ int nabo_project_dense(const float* counts, int ld, int n_cells, const int32_t* 
                        const float* sf, const double* mu, const double* sigma,
                        const double* components, const double* mean, int n_comps, double* out,
                        int ldo, void* stream);
+/* The same dense projection as ONE FP64 tensor-core GEMM (DMMA m8n8k4): the per-gene constants are folded into
+ * W[g][c] = C[c][g] / sigma_g and bias[c] = sum_g (mu_g / sigma_g + mean_g) C[c][g] once per call (workspace),
+ * so P = (a * sf)[f32 -> f64] . W - bias; FP64 accumulate, equal to nabo_project_dense to ~1e-15 relative. */
+size_t nabo_project_dense_workspace_bytes(int G, int n_comps);
+int nabo_project_dense_mma(const float* counts, int ld, int n_cells, const int32_t* gene_idx, int G,
+                           const float* sf, const double* mu, const double* sigma,
+                           const double* components, const double* mean, int n_comps, double* out,
+                           int ldo, void* workspace, size_t workspace_bytes, void* stream);
 size_t nabo_project_csr_workspace_bytes(int G, int n_comps);
 int nabo_project_csr(const int64_t* indptr, const int32_t* col, const float* val, int n_cells,
                      const int32_t* gene_pos, int n_genes_total, int G, const float* sf,

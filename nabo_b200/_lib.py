@@ -56,6 +56,8 @@ SIGNATURES: Dict[str, tuple] = {
     "nabo_sparse_row_stats": (_i, [_p, _p, _p, _i, _i, _p, _p, C.c_longlong, _i, _p, _p, _p, _p, _p, _p]),
     "nabo_scale_dense": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p, _i, _p]),
     "nabo_project_dense": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _i, _p]),
+    "nabo_project_dense_workspace_bytes": (_z, [_i, _i]),
+    "nabo_project_dense_mma": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _i, _p, _z, _p]),
     "nabo_project_csr_workspace_bytes": (_z, [_i, _i]),
     "nabo_project_csr": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _i, _p, _z, _p]),
 }

@@ -524,9 +524,11 @@ def sparse_row_stats(indptr, idx, val, pos_of_col, n_dense: int, scale=None, mom
 
 
 # ----------------------------------------------------------------------------- (6) projection
-def project(counts, gene_idx, sf, mu, sigma, components, mean):
+def project(counts, gene_idx, sf, mu, sigma, components, mean, engine: str = "mma", out=None):
     """``get_scaled_values`` + ``transform_pca`` (nabo/_dataset.py:905-913, 1028) on a dense
-    (cells x genes) count block.  ``gene_idx`` = column of each model gene (-1 = missing)."""
+    (cells x genes) count block.  ``gene_idx`` = column of each model gene (-1 = missing).
+    ``engine='mma'``: one FP64 tensor-core GEMM with the per-gene constants folded into the component matrix
+    (``nabo_project_dense_mma``); ``'simple'``: the straightforward FP64 CUDA-core kernel (``nabo_project_dense``)."""
     require_device()
     host = _is_host(counts)
     cd = _dev(counts, torch.float32)
@@ -540,9 +542,17 @@ def project(counts, gene_idx, sf, mu, sigma, components, mean):
         raise ValueError("ERROR: gene_idx, mu, sigma, mean and components disagree on the number of genes")
     if sfd.numel() != n:
         raise ValueError("ERROR: one size factor per cell is required")
-    out = torch.empty((n, nc), dtype=torch.float64, device=cd.device)
-    check(lib().nabo_project_dense(_ptr(cd), ld, n, _ptr(gi), G, _ptr(sfd), _ptr(mud), _ptr(sgd), _ptr(cm),
-                                   _ptr(mn), nc, _ptr(out), nc, C.c_void_p(_stream())), "project_dense")
+    if out is None:
+        out = torch.empty((n, nc), dtype=torch.float64, device=cd.device)
+    if engine == "simple":
+        check(lib().nabo_project_dense(_ptr(cd), ld, n, _ptr(gi), G, _ptr(sfd), _ptr(mud), _ptr(sgd), _ptr(cm),
+                                       _ptr(mn), nc, _ptr(out), nc, C.c_void_p(_stream())), "project_dense")
+    else:
+        L = lib()
+        ws = torch.empty(int(L.nabo_project_dense_workspace_bytes(G, nc)), dtype=torch.uint8, device=cd.device)
+        check(L.nabo_project_dense_mma(_ptr(cd), ld, n, _ptr(gi), G, _ptr(sfd), _ptr(mud), _ptr(sgd), _ptr(cm),
+                                       _ptr(mn), nc, _ptr(out), nc, _ptr(ws), ws.numel(), C.c_void_p(_stream())),
+              "project_dense_mma")
     return _out(out, host)
 
 

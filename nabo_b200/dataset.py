@@ -247,9 +247,15 @@ class Dataset:
         return True
 
     def fit_ipca(self, genes: List[str], n_comps: int = 100, batch_size: int = None,
-                 disable_tqdm: bool = False) -> None:
-        """nabo/_dataset.py:917-983: scikit-learn IncrementalPCA over the reference's equal-size batches
-        (host; the fit is a one-off per reference and only feeds the path)."""
+                 disable_tqdm: bool = False, *, method: str = "sklearn") -> None:
+        """nabo/_dataset.py:917-983.  ``method='sklearn'`` (default): scikit-learn IncrementalPCA over the
+        reference's equal-size batches on the host - the upstream fit, bit-compatible.  ``method='device'``: the
+        exact PCA of the same scaled values, moments and eigen-decomposition on the GPU (``nabo_b200.pca``); equal
+        to the incremental fit at the level of the subspace."""
+        if method not in ("sklearn", "device"):
+            raise ValueError("ERROR: method must be 'sklearn' or 'device'")
+        if method == "device":
+            return self._fit_pca_device(genes, n_comps)
         from sklearn.decomposition import IncrementalPCA
 
         def make_eq_bins(n, bs):
@@ -286,6 +292,31 @@ class Dataset:
                     pass
         if len(cache) > 0:
             print("WARNING: Not all cells were processed! This is a bug. Please report it to the authors.")
+        self.ipca.genes = list(scaling_params.index)
+        return None
+
+    def _fit_pca_device(self, genes: List[str], n_comps: int, chunk: int = 8192) -> None:
+        import torch
+        from .pca import DevicePCA, MomentAccumulator
+        n_comps = int(n_comps)
+        if len(genes) < n_comps:
+            n_comps = len(genes)
+            print("WARNING: Number of components were reset to number of features i.e. %d" % n_comps)
+        if n_comps > len(self.keepCellsIdx):
+            n_comps = len(self.keepCellsIdx) - 1
+            print("WARNING: Number of components were reset to number of cells - 1 i.e. %d" % n_comps)
+        scaling_params = self.get_scaling_params(genes)
+        mu = torch.from_numpy(scaling_params["mu"].values.astype(np.float64)).cuda()
+        sigma = torch.from_numpy(scaling_params["sigma"].values.astype(np.float64)).cuda()
+        goi = torch.from_numpy(self._gene_order(scaling_params, False)).cuda()
+        keep = np.asarray(self.keepCellsIdx)
+        acc = MomentAccumulator(len(scaling_params), mu.device)
+        for s in range(0, len(keep), chunk):
+            rows = keep[s:s + chunk]
+            z = core.scale_counts(torch.from_numpy(self._dense(rows)).cuda(), goi,
+                                  torch.from_numpy(self.sf[rows].astype(np.float32)).cuda(), mu, sigma)
+            acc.add(z)
+        self.ipca = DevicePCA(n_comps).fit_moments(acc)
         self.ipca.genes = list(scaling_params.index)
         return None
 

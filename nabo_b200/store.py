@@ -465,10 +465,134 @@ def _reroot(g: Group, root: Group):
             _reroot(v, root)
 
 
-def open_file(fn: str, mode: str = "r", **kw):
-    """Single entry point the facade uses to open dataset / PCA / mapping files.
+# ----------------------------------------------------------------------------- real HDF5 where h5py exists
+ROWGROUP_ATTR = "nabo_b200_layout"          # attribute marking an HDF5 group that stores a RowGroup
+ROWGROUP_NAMES, ROWGROUP_ROWS = "names", "rows"
 
-    h5py is absent from the target image, so this always returns the container
-    above; a real-HDF5 backend (RowGroup = one 2-D dataset + a names dataset)
-    plugs in here without touching the callers."""
+
+def _h5py():
+    """The h5py module, or None (absent from the target image).  NABO_B200_STORE=container forces the zip/npy
+    container even where h5py is importable."""
+    if os.environ.get("NABO_B200_STORE", "") == "container":
+        return None
+    try:
+        import h5py
+        return h5py
+    except Exception:
+        return None
+
+
+class H5Group:
+    """The same call surface as ``Group`` on top of an ``h5py`` group: files are real HDF5 with the reference's
+    group / dataset names (nabo/_mapping.py:252-273, 340-355; nabo/_dataset.py:1028).  A ``RowGroup`` is stored as
+    an HDF5 group with the attribute ``nabo_b200_layout = 'rowgroup'`` holding ``rows`` (one 2-D dataset) and
+    ``names`` (byte strings); per-node graph groups written with ``graph_layout='reference'`` are plain HDF5
+    datasets that upstream nabo opens directly."""
+
+    def __init__(self, node, h5):
+        self._g, self._h5 = node, h5
+        self.name = node.name
+
+    def _wrap(self, obj):
+        if isinstance(obj, self._h5.Group):
+            kind = obj.attrs.get(ROWGROUP_ATTR, "")
+            if isinstance(kind, bytes):
+                kind = kind.decode("utf-8")
+            if kind == "rowgroup":
+                return RowGroup(obj.name, None, list(obj[ROWGROUP_NAMES][:]), obj[ROWGROUP_ROWS][:])
+            return H5Group(obj, self._h5)
+        return obj                                      # h5py.Dataset: slicing, fields, shape, dtype as upstream
+
+    def __contains__(self, path) -> bool:
+        return isinstance(path, str) and path in self._g
+
+    def __getitem__(self, path: str):
+        return self._wrap(self._g[path])
+
+    def __delitem__(self, path: str):
+        del self._g[path]
+
+    def __iter__(self) -> Iterator[str]:
+        return iter(sorted(self._g.keys()))
+
+    def __len__(self):
+        return len(self._g)
+
+    def keys(self):
+        return sorted(self._g.keys())
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def create_group(self, path: str) -> "H5Group":
+        return H5Group(self._g.create_group(path), self._h5)
+
+    def require_group(self, path: str) -> "H5Group":
+        return self[path] if path in self else self.create_group(path)
+
+    def create_dataset(self, path: str, shape=None, dtype=None, data=None, **kw):
+        if data is not None:
+            data = np.asarray(data) if dtype is None else np.asarray(data, dtype=dtype)
+            if data.dtype.kind == "U":                  # h5py has no fixed-width unicode: bytes, as on this path upstream
+                data = np.char.encode(data, "utf-8")
+            return self._g.create_dataset(path, data=data, **kw)
+        return self._g.create_dataset(path, shape=shape, dtype=dtype if dtype is not None else np.float32, **kw)
+
+    def create_row_group(self, path: str, names: List[str], data: np.ndarray) -> "RowGroup":
+        g = self._g.create_group(path)
+        g.attrs[ROWGROUP_ATTR] = "rowgroup"
+        data = np.asarray(data)
+        enc = np.char.encode(np.asarray([n.decode("utf-8") if isinstance(n, bytes) else str(n) for n in names], dtype=str),
+                             "utf-8") if len(names) else np.zeros(0, "S1")
+        g.create_dataset(ROWGROUP_NAMES, data=enc)
+        g.create_dataset(ROWGROUP_ROWS, data=data)
+        return RowGroup(g.name, None, list(names), data)
+
+    def __repr__(self):
+        return "<store.H5Group %r (%d members)>" % (self.name, len(self))
+
+
+class H5File(H5Group):
+    """``h5py.File`` behind the ``File`` call surface (mode letters r, r+, a, w, w-/x)."""
+
+    def __init__(self, fn: str, mode: str, h5):
+        self._f = h5.File(str(fn), mode)
+        super().__init__(self._f, h5)
+        self.filename, self.mode = str(fn), mode
+
+    def flush(self):
+        if self.mode != "r":
+            self._f.flush()
+
+    def close(self):
+        try:
+            self._f.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+def _is_container(fn: str) -> bool:
+    try:
+        return os.path.getsize(fn) > 0 and zipfile.is_zipfile(fn)
+    except OSError:
+        return False
+
+
+def open_file(fn: str, mode: str = "r", **kw):
+    """Single entry point the facade uses to open dataset / PCA / mapping files ("h5py when
+    importable"): real HDF5 through ``H5File`` where h5py exists, otherwise the zip/npy container ``File`` with
+    the same group / dataset names.  A file that already is a container stays one (it is never re-read as HDF5)."""
+    h5 = None if (_MEMORY_ONLY or str(fn) in MEMORY_FILES) else _h5py()
+    if h5 is not None and not _is_container(str(fn)) and _DEFERRED.get(os.path.abspath(str(fn))) is None:
+        return H5File(fn, mode, h5)
     return File(fn, mode=mode)

@@ -297,9 +297,64 @@ def golden_c1(nabo, out, tmp):
     print("mapping_c1.npz written")
 
 
+# ---------------------------------------------------------------- E: config 1 through Dataset -> Mapping -> Graph
+def golden_c1_chain(nabo, out, tmp):
+    """BASELINE config 1 at its stated shape through the whole reference chain: 5 000 reference + 5 000 target
+    cells, 2 000 HVGs (of 2 400 genes), IncrementalPCA with 25 components, k = 10: Dataset.set_sf / set_gene_stats /
+    fit_ipca / transform_pca -> Mapping.make_ref_graph / map_target -> Graph.get_mapping_score."""
+    ng, n, nhvg, nc, k = 2400, 5000, 2000, 25, 10
+    cr = synth.nb_counts(n, ng, seed=1)
+    ct = synth.nb_counts(n, ng, seed=101)
+    genes = ["G%04d" % i for i in range(ng)]
+    rn, tn = synth.cell_names(n, "R"), synth.cell_names(n, "T")
+    rfn, tfn = os.path.join(tmp, "e_ref.h5"), os.path.join(tmp, "e_tgt.h5")
+    write_dataset_file(rfn, cr, rn, genes)
+    write_dataset_file(tfn, ct, tn, genes)
+
+    def prep(fn):
+        d = nabo.Dataset(fn, force_recalc=True)
+        d.set_sf()
+        d.set_gene_stats()
+        gs = d.geneStats
+        for c in ("m", "nzm", "variance", "ncells"):
+            gs[c] = gs[c].astype(np.float64)
+        gs["valid_gene"] = gs["valid_gene"].astype(bool)
+        return d
+
+    dr, dt = prep(rfn), prep(tfn)
+    valid = dr.geneStats[dr.geneStats.valid_gene]
+    disp = (valid.variance / valid.m).sort_values(ascending=False)
+    hvg = [g for g in disp.index if dt.geneStats.valid_gene[g]][:nhvg]
+    dr.fit_ipca(hvg, n_comps=nc, disable_tqdm=True)
+    sp = dr.get_scaling_params(hvg)
+    pr_fn, pt_fn = os.path.join(tmp, "e_ref_pca.h5"), os.path.join(tmp, "e_tgt_pca.h5")
+    dr.transform_pca(pr_fn, "data", dr.ipca, sp, disable_tqdm=True)
+    dt.transform_pca(pt_fn, "data", dr.ipca, sp, disable_tqdm=True)
+    h = store.File(pr_fn, "r")
+    pr = np.array([h["data"][c][:] for c in rn])
+    h.close()
+    h = store.File(pt_fn, "r")
+    pt = np.array([h["data"][c][:] for c in tn])
+    h.close()
+    res = run_mapping(nabo, tmp, pr, pt, rn, tn, use_comps=nc, k=k, f=0.25, chunk=1000, tag="e", specificity=False)
+    rs, ts = res["ref_sorted_full"][:, :k + 1], res["tgt_sorted_full"][:, :k + 1]      # one rank past k: tie margin
+    gidx = np.array([genes.index(g) for g in sp.index], dtype=np.int16)
+    np.savez_compressed(
+        os.path.join(out, "chain_c1.npz"), n=n, n_genes=ng, n_hvg=len(hvg), n_comps=nc, k=k, f=0.25,
+        counts_sha=np.array(synth.sha256_of(cr, ct)), gene_idx=gidx,
+        sf_ref=dr.sf, sf_tgt=dt.sf, mu=sp["mu"].values.astype(np.float64), sigma=sp["sigma"].values.astype(np.float64),
+        components=dr.ipca.components_, mean=dr.ipca.mean_,
+        pca_ref=pr, pca_tgt=pt, ref_knn=rs.astype(np.uint16), tgt_knn=ts.astype(np.uint16),
+        ref_knn_dist=np.take_along_axis(res["ref_dist_full"], rs.astype(np.int64), 1),
+        tgt_knn_dist=np.take_along_axis(res["tgt_dist_full"], ts.astype(np.int64), 1),
+        tgt_edge_t=res["tgt_edge_t"].astype(np.uint16), tgt_edge_r=res["tgt_edge_r"].astype(np.uint16),
+        tgt_edge_w=res["tgt_edge_w"].astype(np.float32), score_default=res["score_default"])
+    print("chain_c1.npz: hvg %d, pca %s" % (len(hvg), pr.shape))
+
+
 if __name__ == "__main__":
     nabo = install_shims()
-    which = sys.argv[1:] or ["kernels", "mapping", "edge", "dataset", "c1"]
+    which = sys.argv[1:] or ["kernels", "mapping", "edge", "dataset", "c1", "chain"]
     with tempfile.TemporaryDirectory() as tmp:
         if "kernels" in which:
             golden_kernels(nabo, HERE)
@@ -311,3 +366,5 @@ if __name__ == "__main__":
             golden_dataset(nabo, HERE, tmp)
         if "c1" in which:
             golden_c1(nabo, HERE, tmp)
+        if "chain" in which:
+            golden_c1_chain(nabo, HERE, tmp)

@@ -368,3 +368,111 @@ def test_reference_graph_layout_roundtrip(tmp_path, golden):
     assert np.array_equal(got_sp, g["specificity_raw"], equal_nan=True)
     with pytest.raises(ValueError, match="graph_layout"):
         m.calc_snn("x", "TGT", "y", graph_layout="hdf4")
+
+
+def test_config1_chain_through_the_facade(tmp_path, golden):
+    """BASELINE config 1 at its stated shape through Dataset.fit_ipca -> transform_pca -> Mapping -> Graph on the
+    GPU, against the golden dump of the unmodified reference run on the same counts (chain_c1.npz)."""
+    from nabo_b200 import Dataset, Graph, Mapping, store, synth
+    from nabo_b200.dataset import write_dataset
+    g = golden("chain_c1")
+    n, ng, k, nc, f = int(g["n"]), int(g["n_genes"]), int(g["k"]), int(g["n_comps"]), float(g["f"])
+    cr, ct = synth.nb_counts(n, ng, seed=1), synth.nb_counts(n, ng, seed=101)
+    assert synth.sha256_of(cr, ct) == str(g["counts_sha"])
+    genes = ["G%04d" % i for i in range(ng)]
+    rn, tn = synth.cell_names(n, "R"), synth.cell_names(n, "T")
+    rfn, tfn = str(tmp_path / "r.h5"), str(tmp_path / "t.h5")
+    write_dataset(rfn, cr, rn, genes)
+    write_dataset(tfn, ct, tn, genes)
+    dr, dt = Dataset(rfn, force_recalc=True), Dataset(tfn, force_recalc=True)
+    for d in (dr, dt):
+        d.set_sf()
+        d.set_gene_stats()
+    assert np.array_equal(dr.sf[dr.keepCellsIdx], g["sf_ref"]) and np.array_equal(dt.sf[dt.keepCellsIdx], g["sf_tgt"])
+    hvg = [genes[i] for i in g["gene_idx"]]
+    sp = dr.get_scaling_params(hvg)
+    assert np.array_equal(sp["mu"].values, g["mu"]) and np.array_equal(sp["sigma"].values, g["sigma"])
+    dr.fit_ipca(hvg, n_comps=nc, disable_tqdm=True)                 # upstream's incremental fit, same batches
+    np.testing.assert_allclose(dr.ipca.components_, g["components"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(dr.ipca.mean_, g["mean"], rtol=0, atol=1e-12)
+    pr_fn, pt_fn, map_fn = (str(tmp_path / x) for x in ("pr.h5", "pt.h5", "map.h5"))
+    dr.transform_pca(pr_fn, "data", dr.ipca, sp, disable_tqdm=True)
+    dt.transform_pca(pt_fn, "data", dr.ipca, sp, disable_tqdm=True)
+    for fn, names, exp in ((pr_fn, rn, g["pca_ref"]), (pt_fn, tn, g["pca_tgt"])):
+        h = store.open_file(fn, "r")
+        got = np.array([h["data"][c][:] for c in names])
+        h.close()
+        np.testing.assert_allclose(got, exp, rtol=0, atol=1e-9 * np.abs(exp).max())
+    random.seed(5)
+    m = Mapping(map_fn, "REF", pr_fn, "data", overwrite=True)
+    m.set_parameters(nc, k, f, 1000)
+    m.make_ref_graph()
+    m.map_target("TGT", pt_fn, "data")
+    h5 = store.open_file(map_fn, "r")
+    ruid = h5["name_stash/ref_name"][1].decode()
+    tuid = [i[1].decode() for i in h5["name_stash/target_names"] if i[0] == b"TGT"][0]
+    rk = np.array([h5[ruid + "_sortedDist"][c][:k] for c in rn])
+    tk = np.array([h5[tuid + "_sortedDist"][c][:k] for c in tn])
+    td = np.array([h5[tuid + "_dist"][c][:k] for c in tn])
+    h5.close()
+    # no tie at the k-th rank in this golden (smallest gap 1.5e-7) and the coordinates agree to ~1e-13: same lists
+    assert np.array_equal(rk, g["ref_knn"][:, :k]) and np.array_equal(tk, g["tgt_knn"][:, :k])
+    np.testing.assert_allclose(td, g["tgt_knn_dist"][:, :k], rtol=1e-9)
+    gph = Graph()
+    gph.load_from_h5(map_fn, "REF", "reference")
+    gph.load_from_h5(map_fn, "TGT", "target")
+    exp = {(tn[int(t)] + "_TGT", rn[int(r)] + "_REF"): float(w)
+           for t, r, w in zip(g["tgt_edge_t"], g["tgt_edge_r"], g["tgt_edge_w"])}
+    got = {(a, b) if a.endswith("_TGT") else (b, a): float(np.float32(d["weight"]))
+           for a, b, d in gph.edges(data=True) if a.endswith("_TGT") or b.endswith("_TGT")}
+    assert got == exp
+    sc = gph.get_mapping_score("TGT")
+    np.testing.assert_allclose(np.array([sc[c + "_REF"] for c in rn]), g["score_default"], rtol=1e-12)
+
+
+def test_device_pca_fit_matches_sklearn(tmp_path, golden):
+    """Dataset.fit_ipca(method='device'): moments + eigen-decomposition on the GPU.  Against scikit-learn's exact PCA
+    of the same scaled values: components equal (sign convention included) to 1e-8, principal angles <= 1e-8;
+    against upstream's IncrementalPCA with one batch (which is exact) likewise; with upstream's default batches the
+    incremental fit is an approximation of this decomposition and captures no more variance than it."""
+    from sklearn.decomposition import PCA, IncrementalPCA
+    from nabo_b200 import Dataset
+    from nabo_b200.dataset import write_dataset
+    g = golden("dataset_small")
+    counts = g["counts_ref"].astype(np.int64)
+    genes = ["G%04d" % i for i in range(counts.shape[1])]
+    rn = ["R%04d" % i for i in range(counts.shape[0])]
+    fn = str(tmp_path / "r.h5")
+    write_dataset(fn, counts, rn, genes)
+    d = Dataset(fn, force_recalc=True)
+    d.set_sf()
+    d.set_gene_stats()
+    hvg = [genes[i] for i in g["gene_idx"]]
+    nc = 20
+    d.fit_ipca(hvg, n_comps=nc, disable_tqdm=True, method="device")
+    dev = d.ipca
+    assert dev.genes == hvg and dev.components_.shape == (nc, len(hvg)) and dev.whiten is False
+    z = np.array([a for _, a in d.get_scaled_values(d.get_scaling_params(hvg), disable_tqdm=True)])
+    ref = PCA(n_components=nc, svd_solver="full").fit(z)
+
+    def max_angle(a, b):
+        s = np.linalg.svd(a @ b.T, compute_uv=False)
+        return float(np.arccos(np.clip(s.min(), -1.0, 1.0)))
+    assert max_angle(dev.components_, ref.components_) <= 1e-7
+    np.testing.assert_allclose(dev.components_, ref.components_, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(dev.mean_, ref.mean_, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(dev.explained_variance_, ref.explained_variance_, rtol=1e-10)
+    np.testing.assert_allclose(dev.singular_values_, ref.singular_values_, rtol=1e-10)
+    np.testing.assert_allclose(dev.explained_variance_ratio_, ref.explained_variance_ratio_, rtol=1e-10)
+    np.testing.assert_allclose(dev.transform(z[:7]), ref.transform(z[:7]), rtol=0, atol=1e-9)
+    one = IncrementalPCA(n_components=nc, batch_size=len(z)).fit(z)
+    np.testing.assert_allclose(dev.components_, one.components_, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(dev.var_, one.var_, rtol=1e-10)
+    # upstream's default schedule (batches of 2 * n_comps) truncates after every batch: an approximation (on this
+    # nearly flat spectrum its axes are up to ~0.5 rad off the exact ones); the exact fit can only capture more variance
+    zc = z - z.mean(0)
+    captured = lambda c: float(((zc @ c.T) ** 2).sum())
+    assert captured(dev.components_) >= captured(g["components"]) * (1 - 1e-12)
+    # the model drops into transform_pca
+    out = str(tmp_path / "p.h5")
+    d.transform_pca(out, "data", dev, d.get_scaling_params(hvg), disable_tqdm=True)

@@ -230,3 +230,29 @@ def test_edge_semantics_of_the_reference(golden):
     assert (od[[4, 5, 6], :n_live] == uc).all()
     full = O.mod_canberra_dist(g["tgt"][:, :uc], g["ref"][:, :uc], f)
     assert np.array_equal(full, g["tgt_dist_full"])          # incl. the NaN-coordinate target and the zero target
+
+
+def test_config1_chain_golden(golden):
+    """BASELINE config 1 at its stated shape (5 000 + 5 000 cells, 2 000 HVGs, 25 PCs, k = 10) through the whole
+    reference chain Dataset -> Mapping -> Graph (tests/golden/make_golden.py::golden_c1_chain): the oracle, fed the
+    regenerated counts and the reference's model, reproduces the projection, both neighbour tables, the target
+    edges with their weights and the mapping scores."""
+    from nabo_b200 import synth
+    g = golden("chain_c1")
+    n, ng, k = int(g["n"]), int(g["n_genes"]), int(g["k"])
+    cr, ct = synth.nb_counts(n, ng, seed=1), synth.nb_counts(n, ng, seed=101)
+    assert synth.sha256_of(cr, ct) == str(g["counts_sha"])
+    gi = g["gene_idx"].astype(np.int64)
+    for counts, sf, exp in ((cr, g["sf_ref"], g["pca_ref"]), (ct, g["sf_tgt"], g["pca_tgt"])):
+        p = O.project(counts[:, gi], sf, g["mu"], g["sigma"], g["components"], g["mean"])
+        np.testing.assert_allclose(p, exp, rtol=0, atol=1e-12 * np.abs(exp).max())
+    ri, rd = O.knn(g["pca_ref"], g["pca_ref"], k, "euclidean", drop_first=True)
+    ti, td = O.knn(g["pca_tgt"], g["pca_ref"], k, "mod_canberra", float(g["f"]))
+    assert np.array_equal(ri, g["ref_knn"][:, :k]) and np.array_equal(rd, g["ref_knn_dist"][:, :k])
+    assert np.array_equal(ti, g["tgt_knn"][:, :k]) and np.array_equal(td, g["tgt_knn_dist"][:, :k])
+    cnt, w = O.snn_weights(ti, ri, k)
+    t, j = np.nonzero(cnt > 0)
+    got = sorted(zip(t.tolist(), ti[t, j].tolist(), w[t, j].astype(np.float32).tolist()))
+    exp = sorted(zip(g["tgt_edge_t"].tolist(), g["tgt_edge_r"].tolist(), g["tgt_edge_w"].tolist()))
+    assert got == exp
+    np.testing.assert_allclose(O.mapping_scores(ti, w, n, counts=cnt), g["score_default"], rtol=1e-12)

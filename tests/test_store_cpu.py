@@ -239,3 +239,125 @@ def test_weight_table_for_k2_is_lazy():
         core.snn_weight_lut(2)
     assert core.snn_int_weights(2).tolist() == [0, 100, 0]
     assert core.snn_weight_lut(1).tolist() == [0.0, -1.0]
+
+
+# ----------------------------------------------------------------------------- h5py backend of store.open_file
+class _FakeH5:
+    """Minimal in-memory stand-in with h5py's object model (Group with .attrs / create_group / create_dataset /
+    [] with a/b paths / del / keys, Dataset with slicing) so that the H5File adapter is exercised in this image,
+    where h5py itself is absent.  The real-HDF5 round trip below runs wherever h5py is importable."""
+    files = {}
+
+    class Dataset:
+        def __init__(self, data, name):
+            self._a, self.name = np.array(data), name
+        shape = property(lambda s: s._a.shape)
+        dtype = property(lambda s: s._a.dtype)
+        def __len__(self): return len(self._a)
+        def __getitem__(self, k): return self._a[k]
+        def __setitem__(self, k, v): self._a[k] = v
+        def __iter__(self): return iter(self._a)
+        def __array__(self, dtype=None, copy=None): return self._a if dtype is None else self._a.astype(dtype)
+
+    class Group:
+        def __init__(self, name="/"):
+            self.name, self.attrs, self._c = name, {}, {}
+        def _walk(self, path, create=False):
+            node = self
+            parts = [p for p in path.split("/") if p]
+            for p in parts[:-1]:
+                if p not in node._c:
+                    if not create:
+                        raise KeyError(path)
+                    node._c[p] = _FakeH5.Group(node.name.rstrip("/") + "/" + p)
+                node = node._c[p]
+            return node, parts[-1]
+        def __contains__(self, path):
+            try:
+                node, leaf = self._walk(path)
+            except KeyError:
+                return False
+            return leaf in node._c
+        def __getitem__(self, path):
+            node, leaf = self._walk(path)
+            return node._c[leaf]
+        def __delitem__(self, path):
+            node, leaf = self._walk(path)
+            del node._c[leaf]
+        def __len__(self): return len(self._c)
+        def keys(self): return list(self._c.keys())
+        def create_group(self, path):
+            node, leaf = self._walk(path, True)
+            if leaf in node._c:
+                raise ValueError("exists")
+            node._c[leaf] = _FakeH5.Group(node.name.rstrip("/") + "/" + leaf)
+            return node._c[leaf]
+        def create_dataset(self, path, shape=None, dtype=None, data=None, **kw):
+            node, leaf = self._walk(path, True)
+            if leaf in node._c:
+                raise ValueError("exists")
+            arr = np.zeros(shape, dtype) if data is None else np.array(data, dtype=dtype)
+            assert arr.dtype.kind != "U", "h5py cannot store fixed-width unicode"
+            node._c[leaf] = _FakeH5.Dataset(arr, node.name.rstrip("/") + "/" + leaf)
+            return node._c[leaf]
+
+    class File(Group):
+        def __init__(self, fn, mode="r"):
+            super().__init__("/")
+            if mode in ("r", "r+") and fn not in _FakeH5.files:
+                raise OSError("no such file")
+            if mode == "w" or fn not in _FakeH5.files:
+                _FakeH5.files[fn] = ({}, {})
+                open(fn, "ab").close()
+            self._c, self.attrs = _FakeH5.files[fn]
+        def flush(self): pass
+        def close(self): pass
+
+
+def _h5_roundtrip(tmp_path, monkeypatch, module):
+    from nabo_b200 import store
+    monkeypatch.setattr(store, "_h5py", lambda: module)
+    fn = str(tmp_path / "real.h5")
+    h = store.open_file(fn, "w")
+    assert isinstance(h, store.H5File)
+    h.create_group("name_stash").create_dataset("ref_name", data=[b"REF", b"abc"])
+    h["name_stash"].create_dataset("target_names", data=[[b"T1", b"u1"], [b"T2", b"u2"]])
+    h.create_dataset("g/x", data=np.arange(6.0).reshape(2, 3))
+    h.create_dataset("g/names", data=np.array(["b", "a"]))                 # unicode in -> bytes stored
+    h.create_row_group("uid_sortedDist", ["c2", "c1"], np.array([[3, 4], [5, 6]], dtype=np.int64))
+    node = h.create_group("uid_graph")                                      # the reference's per-node layout
+    node.create_dataset("c1_T", data=np.array([(b"c9_REF", 0.25), (b"c8_REF", 0.5)]))
+    h.flush()
+    h.close()
+    h = store.open_file(fn, "r")
+    assert h["name_stash/ref_name"][0] == b"REF" and h["name_stash/target_names"][:][1][1] == b"u2"
+    assert h["g/x"][:].tolist() == [[0, 1, 2], [3, 4, 5]] and h["g/names"][:].tolist() == [b"b", b"a"]
+    assert "uid_sortedDist" in h and "nope" not in h and list(h["g"]) == ["names", "x"]
+    rg = h["uid_sortedDist"]
+    assert isinstance(rg, store.RowGroup) and list(rg) == ["c1", "c2"] and rg["c2"][:2].tolist() == [3, 4]
+    row = h["uid_graph/c1_T"][:]
+    assert row.dtype.kind == "S" and row[0][0] == b"c9_REF" and float(row[1][1]) == 0.5
+    h.close()
+    h = store.open_file(fn, "a")
+    del h["g/x"]
+    assert "g/x" not in h
+    h.close()
+
+
+def test_h5py_backend_adapter_with_stand_in(tmp_path, monkeypatch):
+    _FakeH5.files.clear()
+    _h5_roundtrip(tmp_path, monkeypatch, _FakeH5)
+    # a file that already is a zip/npy container stays one even where h5py exists
+    from nabo_b200 import store
+    monkeypatch.setattr(store, "_h5py", lambda: None)
+    fn = str(tmp_path / "container.h5")
+    h = store.open_file(fn, "w")
+    h.create_dataset("x", data=np.arange(3))
+    h.close()
+    monkeypatch.setattr(store, "_h5py", lambda: _FakeH5)
+    assert isinstance(store.open_file(fn, "r"), store.File)
+
+
+def test_h5py_backend_real_hdf5(tmp_path, monkeypatch):
+    h5py = pytest.importorskip("h5py")
+    _h5_roundtrip(tmp_path, monkeypatch, h5py)
