@@ -53,6 +53,11 @@ def parse():
                          "(no collective); reference: every GPU holds --n-ref reference rows of a --gpus x larger "
                          "reference, all GPUs map the same --n-query targets, candidates are all-gathered and merged "
                          "(BASELINE config 4)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
+                    help="config2 (default): the headline line; config5: counts -> projection -> cosine kNN -> scores per sample")
+    ap.add_argument("--c5-cells", type=int, default=500_000)
+    ap.add_argument("--c5-ref", type=int, default=2_000_000)
+    ap.add_argument("--c5-genes", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-projection", action="store_true", help="skip the projection (A1/A2) measurement")
     ap.add_argument("--no-ref-sharded", action="store_true", help="skip the reference-sharded (config 4) block")
@@ -67,22 +72,23 @@ WORKLOAD = "config2: {nq} target x {nr} reference cells, {g} PCs, k={k}, {metric
 
 
 def canberra_roofline(g, n, m, kernel_ms):
-    """5 FP ops per (pair, dimension), denominator = FP32 CUDA-core pipe (148 SM x 128 lanes x 2 x
-    max SM clock - nominal, there is no measured FP32 peak in MEASURED_PEAKS.json).  The bit-sliced pass
-    (canberra_sliced.cu) never executes most of that work - a pair is rejected by the count bound for
-    3.25 / 32 LOP3 per dimension - so the algorithmic fraction can exceed 1; `executed` therefore also gives
-    the kernel against the pipe that really bounds it: the integer ALU pipe (148 SM x 64 lanes per clock) on
-    the count bound's unavoidable LOP3 (1 interval test + 2.25 carry-save adder ops per 32 references)."""
+    """Roofline of the bit-sliced modified-Canberra candidate pass (canberra_sliced.cu).  The pipe that bounds it is
+    the integer ALU (148 SM x 64 lanes per clock at the max SM clock - nominal, MEASURED_PEAKS.json has no integer
+    figure): a pair is rejected by the count bound for 3.25 / 32 LOP3 per dimension (1 interval test + 2.25
+    carry-save adder ops per 32 references), and `frac` is that EXECUTED work against that pipe.  SURVEY 8(d)'s
+    algorithmic figure (5 FP ops per (pair, dimension) on the FP32 pipe) is kept as a side key: ~98 % of it is
+    never executed, so its ratio to the FP32 peak is not a roofline fraction."""
     t = kernel_ms * 1e-3
-    ach = 5.0 * g * n * m / t / 1e12
-    peak = 148 * 128 * 2 * 1.965e9 / 1e12
     lop = 3.25 / 32.0 * g * n * m / t / 1e12
     lop_peak = 148 * 64 * 1.965e9 / 1e12
-    return {"bound": "fp32", "kernel": "cbs::sliced_kernel", "achieved": ach, "unit": "TFLOP/s", "peak": peak,
-            "frac": ach / peak, "peak_source": "nominal B200 FP32 FMA peak at max SM clock",
-            "note": "algorithmic work of the full metric; the count bound prunes ~98 % of it before the FP32 pipe",
-            "executed": {"bound": "alu", "achieved": lop, "peak": lop_peak, "unit": "TLOP3/s", "frac": lop / lop_peak,
-                         "pairs_per_s": n * m / t},
+    alg = 5.0 * g * n * m / t / 1e12
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    return {"bound": "alu", "kernel": "cbs::sliced_kernel", "achieved": lop, "unit": "TLOP3/s", "peak": lop_peak,
+            "frac": lop / lop_peak, "peak_source": "nominal B200 integer-ALU issue rate at max SM clock",
+            "pairs_per_s": n * m / t,
+            "algorithmic_fp32": {"achieved": alg, "unit": "TFLOP/s", "nominal_fp32_peak": fp32_peak,
+                                 "note": "5 FP ops per (pair, dimension) of the full metric; the count bound prunes "
+                                         "~98 % of it before the FP32 pipe, so achieved / peak is not a fraction of a roof"},
             "traffic": None}
 
 
@@ -445,6 +451,126 @@ def score_determinism_check(dev, rank, world, ref, ref_knn, k, n_targets=65_536)
             "scores_sha256": hashlib.sha256(single.cpu().numpy().tobytes()).hexdigest()}
 
 
+def run_b200_config5(a):
+    """BASELINE config 5 (`--workload config5`): 8 target samples x --c5-cells cells of raw counts (--c5-genes HVG
+    columns) against a --c5-ref-cell reference in 50-PC space, cosine, k = 30, target-sharded: rank r maps samples
+    r, r + world, ...  One step = one sample through the whole path: counts -> scaling + projection (FP64 tensor-core
+    GEMM) -> cosine kNN (tcgen05 candidates + FP64 re-rank) -> SNN weights -> integer score accumulation.  The
+    per-reference scores of all samples are all-reduced once at the end (integers: same bits for any GPU count)."""
+    import torch
+    import torch.distributed as dist
+    from nabo_b200 import build, core, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus > 1 and world != a.gpus:
+        raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (a.gpus, a.gpus, world))
+    build.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    M, N, G, nc, k, n_samples = a.c5_ref, a.c5_cells, a.c5_genes, a.comps, a.k, 8
+    t0 = time.perf_counter()
+    ref = synth.pc_mixture_device(M, nc, seed=1, device=dev)
+    ref_knn = torch.empty((M, k), dtype=torch.int32, device=dev)
+    for lo in range(0, M, 500_000):                                  # make_ref_graph's table, cosine
+        hi = min(M, lo + 500_000)
+        ref_knn[lo:hi] = core.knn(ref[lo:hi], ref, k + 1, "cosine", mode=a.engine)[0][:, 1:]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    comps = torch.linalg.qr(torch.randn((G, nc), generator=gen, device=dev, dtype=torch.float64))[0].T.contiguous()
+    mean = 0.1 * torch.randn(G, generator=gen, device=dev, dtype=torch.float64)
+    probe = synth.nb_counts_device(4096, G, seed=99, device=dev)
+    ptot = probe.sum(1)
+    x = probe * (1000.0 / torch.where(ptot > 0, ptot, torch.ones_like(ptot)))[:, None]
+    mu, sigma = x.mean(0).to(torch.float64), x.std(0).to(torch.float64) + 1e-3
+    gi = torch.arange(G, dtype=torch.int32, device=dev)
+    mine = list(range(rank, n_samples, world))
+    samples = []
+    for s_ in mine:
+        c = synth.nb_counts_device(N, G, seed=100 + s_, device=dev)
+        tot = c.sum(1)
+        samples.append((c, (1000.0 / torch.where(tot > 0, tot, torch.ones_like(tot))).to(torch.float32)))
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    acc = torch.zeros(M, dtype=torch.int64, device=dev)
+    pca = torch.empty((N, nc), dtype=torch.float64, device=dev)
+    stage = {n_: [] for n_ in ("projection", "knn", "snn", "scores")}
+
+    def step(i, timed_stages=False):
+        counts, sf = samples[i % len(samples)]
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timed_stages else None
+        if marks: marks[0].record()
+        core.project(counts, gi, sf, mu, sigma, comps, mean, engine="mma", out=pca)
+        if marks: marks[1].record()
+        idx, dst = core.knn(pca, ref, k, "cosine", mode=a.engine)
+        if marks: marks[2].record()
+        cnt, w = core.snn_weights(idx, ref_knn, k)
+        if marks: marks[3].record()
+        core.score_accumulate(idx, cnt, M, k, acc=acc)
+        if marks:
+            marks[4].record()
+            for j, n_ in enumerate(("projection", "knn", "snn", "scores")):
+                stage[n_].append((marks[j], marks[j + 1]))
+        return idx, dst, w
+
+    for i in range(a.warmup):
+        step(i)
+    acc.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    for i in range(a.steps):
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([sum(_ev_ms(ev))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    scores = core.scores_finalize(acc, world * a.steps * N)
+    for i in range(min(2, a.steps)):
+        step(i, timed_stages=True)
+    torch.cuda.synchronize()
+    ms_step = float(t.item()) / a.steps
+    peaks = load_peaks()
+    line = {
+        "metric": "target_cells_mapped_per_s", "value": world * N / (ms_step / 1e3), "unit": "cells/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 (projection: f64 DMMA; candidates: f16x2-split tcgen05, f32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": "config5: %d samples x %d cells x %d HVG counts -> %d PCs -> cosine kNN (k=%d) against %d "
+                               "reference cells -> SNN weights -> mapping scores; target-sharded, %d sample(s) per GPU"
+                               % (n_samples, N, G, nc, k, M, len(mine)),
+                   "engine": a.engine, "l2": "inputs (4 GB of counts per sample) exceed L2", "inputs_resident": True},
+        "clocks": clocks,
+        "stage_ms": {n_: sum(_ev_ms(p_)) / max(1, len(p_)) for n_, p_ in stage.items()},
+        "projection_tflops_fp64": 2.0 * G * nc * N / (max(1e-9, sum(_ev_ms(stage["projection"])) / max(1, len(stage["projection"]))) * 1e-3) / 1e12,
+        "knn_pairs_per_s": float(N) * M / (max(1e-9, sum(_ev_ms(stage["knn"])) / max(1, len(stage["knn"]))) * 1e-3),
+        "scores_sha256_note": "integer weight sums all-reduced once; nonzero reference cells: %d" % int((scores > 0).sum()),
+        "e2e": None, "gpu_launches": None, "cpu_baseline": None, "setup_s": setup_s,
+        "roofline": {"bound": "tmem-read / tensor", "kernel": "tc::candidates_kernel", "unit": "TFLOP/s",
+                     "achieved": 2.0 * nc * N * M / (max(1e-9, sum(_ev_ms(stage["knn"])) / max(1, len(stage["knn"]))) * 1e-3) / 1e12,
+                     "peak": peaks["bf16_tflops_sustained"], "traffic": None,
+                     "note": "whole kNN call (candidates + re-rank), 2*g flop per pair"},
+    }
+    line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200_refshard(a):
     """`--shard reference`: only the reference-sharded block, as the whole line."""
     import torch
@@ -582,6 +708,13 @@ def run_b200(a):
                 "unit": "TFLOP/s", "kernel": "tc::candidates_kernel",
                 "peak_source": "%s bf16 burst (kernel timed per launch)" % peaks["source"],
                 "executed_tflops": flops * (((3 * g + 3 + 15) // 16 * 16) / g) / (kern * 1e-3) / 1e12,
+                # the resource that really binds this kernel: every 128 x 128 FP32 accumulator tile has to leave TMEM
+                # through tcgen05.ld at 64 B per clock per SM = 16 pairs per clock per SM, whatever K is
+                "tmem_readout": {"achieved_pairs_per_s": float(N) * M / (kern * 1e-3),
+                                 "peak_pairs_per_s": 148 * 16 * 1.965e9,
+                                 "frac": float(N) * M / (kern * 1e-3) / (148 * 16 * 1.965e9),
+                                 "peak_source": "64 B/clk/SM TMEM read port (B300_MICROARCH.md; reproduced here: the kernel "
+                                                "with selection compiled out runs at 1 049 clk per tile), 148 SMs, max SM clock"},
                 "traffic": None}
     elif a.metric == "mod_canberra" and a.engine == "fast":
         roof = canberra_roofline(g, N, M, kern)
@@ -593,7 +726,9 @@ def run_b200(a):
     roof["frac"] = roof["achieved"] / roof["peak"]
     tr = os.path.join(ROOT, "profiles", "bench_traffic.json")
     if os.path.exists(tr):
-        roof["traffic"] = json.load(open(tr)).get(roof["kernel"])
+        trj = json.load(open(tr))
+        roof["traffic"] = trj.get(roof["kernel"])
+        roof["traffic_source"] = "static, not measured in this run: " + trj.get("source", "profiles/bench_traffic.json")
 
     line = {
         "metric": "target_cells_mapped_per_s", "value": value, "unit": "cells/s", "n_gpus": world,
@@ -624,7 +759,8 @@ def run_b200(a):
                                 "rows_exact_fallback_per_step": sec["fallback"] / sec_steps,
                                 "roofline": canberra_roofline(g, N, M, sk)}
         if os.path.exists(tr):
-            line["mod_canberra"]["roofline"]["traffic"] = json.load(open(tr)).get("cbs::sliced_kernel")
+            line["mod_canberra"]["roofline"]["traffic"] = trj.get("cbs::sliced_kernel")
+            line["mod_canberra"]["roofline"]["traffic_source"] = roof.get("traffic_source")
 
     if not a.no_ref_sharded and a.metric == "euclidean" and a.engine == "fast":
         # BASELINE config 4 under the same clock: world x 1.25 M reference rows, 5 batches of 200 k targets
@@ -654,6 +790,8 @@ if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "config5":
+        run_b200_config5(args)
     elif args.shard == "reference":
         run_b200_refshard(args)
     else:

@@ -325,6 +325,7 @@ sliced_kernel(const Params p) {
             }
             if (active && acc < s_tau[ql]) {
                 const int pos = atomicAdd(&s_cnt[ql], 1);
+                NABO_DEV_ASSERT(pos >= 0 && pos < CAP && ql >= 0 && ql < 32);
                 gbuf[(size_t)ql * CAP + pos] = make_key(acc, (uint32_t)(ref0 + rl));
             }
             __syncwarp();

@@ -1,6 +1,7 @@
 // Shared helpers for the nabo_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <math_constants.h>
 
@@ -27,6 +28,15 @@ int nabo_set_error(int code, const char* fmt, ...);
         if (e__ != cudaSuccess)                                                          \
             return nabo_set_error((int)e__, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
     } while (0)
+
+// -DNABO_CHECK: device-side bounds assertions in the hand-rolled pipelines (candidate-buffer appends, emit, tile
+// indices).  compute-sanitizer is closed on the GPU pool this was developed on, so the test suite is run once
+// against a library built with this switch instead (tools/build_variant.py check -DNABO_CHECK; profiles/).
+#ifdef NABO_CHECK
+#define NABO_DEV_ASSERT(cond) do { if (!(cond)) { printf("NABO_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define NABO_DEV_ASSERT(cond)
+#endif
 
 static inline size_t nabo_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -374,6 +374,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (v[8 * gi + i] < tau) {
+                        NABO_DEV_ASSERT(cnt >= 0 && cnt < CAP);
                         mybuf[cnt] = make_key(v[8 * gi + i], col0 + 8 * gi + i);
                         ++cnt;
                     }
@@ -587,6 +588,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                 ptx::tc_fence_after();
                 TC_CLK_ADD(7, t_w);
                 const int jt = sweep_tile(j, start, p.n_rtiles);  // the reference tile this sweep position holds
+                NABO_DEV_ASSERT(jt >= 0 && jt < p.n_rtiles);
                 const int col_limit = p.n_ref - jt * TILE;       // columns >= col_limit are padding
                 // the compaction of every lane whose buffer passed `lim` (soft limit once per tile, after the
                 // accumulator has been handed back; hard limit otherwise: the next chunk may append 32 more)
@@ -674,6 +676,7 @@ emit_kernel(const Params p, int n_work, int n_seg) {
     if (qp >= p.n_query) return;
     const int n = p.cand_cnt[wq];
     const float old_tau = p.cand_tau[wq];
+    NABO_DEV_ASSERT(n >= 0 && n <= CAP);
     uint32_t ks[4], kpl[4];
     int nc;
     float nt;
