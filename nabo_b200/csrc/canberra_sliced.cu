@@ -339,7 +339,7 @@ sliced_kernel(const Params p) {
                 need &= need - 1;
                 int nc;
                 float nt;
-                compact_select(gbuf + (size_t)src * CAP, s_cnt[src], lane, kprime, trig - 4 > kprime ? trig - 4 : kprime, hist, nc, nt);
+                compact_select<4>(gbuf + (size_t)src * CAP, s_cnt[src], lane, kprime, trig - 4 > kprime ? trig - 4 : kprime, hist, nc, nt);
                 if (lane == src) { s_cnt[lane] = nc; s_tau[lane] = nt; }
                 __syncwarp();
             }
@@ -501,7 +501,7 @@ sliced_kernel(const Params p) {
             uint32_t ks[4], kpl[4];
             int nc;
             float nt;
-            compact_sort_inline(gbuf + (size_t)src * CAP, n, lane, kprime, ks, kpl, nc, nt);
+            compact_sort_inline<4>(gbuf + (size_t)src * CAP, n, lane, kprime, ks, kpl, nc, nt);
             const long long qg = (long long)group * 32 + src;
             if (qg < p.n_query) {
 #pragma unroll

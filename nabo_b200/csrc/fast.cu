@@ -108,8 +108,8 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
     int kprime = 0, launches = 0;
     int n_split = nabo_tc_split(n_query, n_ref);              // > 1 only when there are fewer query items than SMs
     while (n_split > 1 && n_split * nabo_tc_kprime(k, drop_first) > 128) --n_split;     // the re-rank takes <= 128 candidates
-    int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, mask, drop_first, n_split, ar, &cand,
-                                &kprime, &tau, &qn2, &scal, &launches, tm, st);
+    int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, mask, drop_first, &n_split, ar, &cand,
+                                &kprime, &tau, &qn2, &scal, &launches, tm, st);       // n_split out: K' lists per query
     if (rc) return rc;
     int* fail_rows = ar.take<int>(n_query);
     int* fail_count = ar.take<int>(1);

@@ -6,7 +6,8 @@
 
 namespace sel {
 
-constexpr int CAP = 128;   // keys per query buffer (4 per lane)
+constexpr int CAP = 128;   // keys per query buffer of the default instantiations (KPL = 4 keys per lane);
+                           // the tensor-core pass uses KPL = 8 (256 keys): compactions are a quarter as frequent
 
 // buffer key = raw float bits of the score (high word) | local reference index (low word);
 // the compaction routines convert to an order-preserving integer when they load a key
@@ -25,15 +26,16 @@ __device__ __forceinline__ void cex(uint32_t& s0, uint32_t& p0, uint32_t& s1, ui
     if (sw) { uint32_t t = s0; s0 = s1; s1 = t; t = p0; p0 = p1; p1 = t; }
 }
 
-__device__ __forceinline__ void sort128(uint32_t (&s)[4], uint32_t (&pl)[4], int lane) {
+template <int KPL>
+__device__ __forceinline__ void sortn(uint32_t (&s)[KPL], uint32_t (&pl)[KPL], int lane) {
 #pragma unroll
-    for (int size = 2; size <= 128; size <<= 1) {
+    for (int size = 2; size <= 32 * KPL; size <<= 1) {
 #pragma unroll
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             if (stride >= 32) {
                 const int du = stride >> 5;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < KPL; ++u) {
                     if ((u & du) == 0) {
                         const bool up = (((u * 32) & size) == 0);      // lane bits never reach `size` >= 64
                         cex(s[u], pl[u], s[u | du], pl[u | du], up);
@@ -41,7 +43,7 @@ __device__ __forceinline__ void sort128(uint32_t (&s)[4], uint32_t (&pl)[4], int
                 }
             } else {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < KPL; ++u) {
                     const int i = u * 32 + lane;
                     const uint32_t os = __shfl_xor_sync(0xffffffffu, s[u], stride);
                     const uint32_t op = __shfl_xor_sync(0xffffffffu, pl[u], stride);
@@ -55,42 +57,45 @@ __device__ __forceinline__ void sort128(uint32_t (&s)[4], uint32_t (&pl)[4], int
         }
     }
 }
+__device__ __forceinline__ void sort128(uint32_t (&s)[4], uint32_t (&pl)[4], int lane) { sortn<4>(s, pl, lane); }
 
 // Exact compaction: sort lane `src`'s buffer (n live keys), keep the kprime best at the front of the
 // buffer.  New count / threshold come back through nc / nt (valid on every lane); s / pl hold the sorted
 // keys.  Force-inlined where the caller consumes s / pl (the per-item final emit) so that the arrays
 // stay in registers; compact_select uses the out-of-line wrapper below as its rare fallback.
+template <int KPL>
 __device__ __forceinline__ void compact_sort_inline(unsigned long long* gbuf, int n, int lane, int kprime,
-                                                    uint32_t (&s)[4], uint32_t (&pl)[4], int& nc, float& nt) {
+                                                    uint32_t (&s)[KPL], uint32_t (&pl)[KPL], int& nc, float& nt) {
     __syncwarp();            // the owner's appends (plain global stores) are ordered before our loads
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < KPL; ++u) {
         const int i = u * 32 + lane;
         const unsigned long long kv = i < n ? __ldcg(gbuf + i) : 0ull;     // through L2: never a stale L1 line
         s[u] = i < n ? float_to_sortable(__uint_as_float((uint32_t)(kv >> 32))) : 0xffffffffu;
         pl[u] = (uint32_t)kv;
     }
-    sort128(s, pl, lane);
+    sortn<KPL>(s, pl, lane);
     nc = n < kprime ? n : kprime;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < KPL; ++u) {
         const int i = u * 32 + lane;
         if (i < nc) gbuf[i] = ((unsigned long long)__float_as_uint(sortable_to_float(s[u])) << 32) | pl[u];
     }
     // threshold = score of element kprime-1 (only meaningful when n >= kprime)
     const int e = kprime - 1;
     uint32_t ts = s[0];
-    if ((e >> 5) == 1) ts = s[1];
-    if ((e >> 5) == 2) ts = s[2];
-    if ((e >> 5) == 3) ts = s[3];
+#pragma unroll
+    for (int u = 1; u < KPL; ++u)
+        if ((e >> 5) == u) ts = s[u];
     ts = __shfl_sync(0xffffffffu, ts, e & 31);
     nt = n >= kprime ? sortable_to_float(ts) : CUDART_INF_F;
     __syncwarp();
 }
 
+template <int KPL>
 static __device__ __noinline__ void compact_sort(unsigned long long* gbuf, int n, int lane, int kprime, int& nc, float& nt) {
-    uint32_t s[4], pl[4];
-    compact_sort_inline(gbuf, n, lane, kprime, s, pl, nc, nt);
+    uint32_t s[KPL], pl[KPL];
+    compact_sort_inline<KPL>(gbuf, n, lane, kprime, s, pl, nc, nt);
 }
 
 // Cheap running compaction: one 256-bin histogram pass over the scores of the buffer finds a
@@ -100,14 +105,15 @@ static __device__ __noinline__ void compact_sort(unsigned long long* gbuf, int n
 // ("everything rejected or dropped has score >= tau") holds without an exact selection.
 // If the cut keeps more than max_keep keys (ties, duplicates) the exact sort takes over.
 // hist: 256 counters of this warp in shared memory.
+template <int KPL>
 static __device__ __noinline__ void compact_select(unsigned long long* gbuf, int n, int lane, int kprime, int max_keep,
                                             uint32_t* hist, int& nc, float& nt) {
     __syncwarp();
-    float fv[4];
-    uint32_t pl[4];
+    float fv[KPL];
+    uint32_t pl[KPL];
     float flo = CUDART_INF_F, fhi = -CUDART_INF_F;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < KPL; ++u) {
         const int i = u * 32 + lane;
         const unsigned long long kv = i < n ? __ldcg(gbuf + i) : 0ull;
         fv[u] = __uint_as_float((uint32_t)(kv >> 32));
@@ -122,9 +128,9 @@ static __device__ __noinline__ void compact_select(unsigned long long* gbuf, int
     __syncwarp();
     const float range = fhi - flo;
     const float scale = range > 0.f ? 255.999f / range : 0.f;       // monotone map of [flo, fhi] onto bins 0..255
-    int bin[4];
+    int bin[KPL];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < KPL; ++u) {
         const int i = u * 32 + lane;
         bin[u] = max(0, min(255, (int)((fv[u] - flo) * scale)));
         if (i < n) atomicAdd(&hist[bin[u]], 1u);
@@ -162,14 +168,14 @@ static __device__ __noinline__ void compact_select(unsigned long long* gbuf, int
         kept = __shfl_sync(0xffffffffu, k_at, owner);
     }
     if ((int)kept > max_keep) {
-        compact_sort(gbuf, n, lane, kprime, nc, nt);
+        compact_sort<KPL>(gbuf, n, lane, kprime, nc, nt);
         return;
     }
     // stream-compact the kept keys to the front (all keys are in registers: in-place is safe)
     uint32_t base = 0;
     float tmax = -CUDART_INF_F;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < KPL; ++u) {
         const int i = u * 32 + lane;
         const bool keep = i < n && bin[u] <= cut_bin;
         const unsigned m = __ballot_sync(0xffffffffu, keep);

@@ -40,13 +40,21 @@ constexpr int PRODUCER_WARP = 12;    // highest warp ids on their schedulers: th
 constexpr int MMA_WARP0 = 13;        // so the single-thread producer / issuers are never starved;
                                      // warps 13..15: one MMA issuer per query tile (no polling loop)
 constexpr int TMEM_WARP = 12;
-constexpr int CAP = sel::CAP;        // candidate buffer entries per query
+#ifndef NABO_TC_KPL
+#define NABO_TC_KPL 4                // measured with 8 (256-key buffers, a quarter of the compactions): candidate kernel
+#endif                               // 3.78 -> 4.51 ms at 100 k x 100 k (staler thresholds, 2 KB per query in L2) and the
+constexpr int KPL = NABO_TC_KPL;     // final selection 0.17 -> 1.8 ms; it only pays for K' > 56 (k = 60: 55 -> 7.4 ms)
+constexpr int CAP = 32 * KPL;        // candidate buffer entries per query
 constexpr int CHUNK = 32;           // columns per tcgen05.ld
+constexpr int MAX_KPRIME = 96;      // K' lists go to the re-rank, which takes at most 128 candidates per query
 #ifndef NABO_TC_ROTATE
 #define NABO_TC_ROTATE 1
 #endif
 #ifndef NABO_TC_PIPE
 #define NABO_TC_PIPE 0
+#endif
+#ifndef NABO_TC_SLEEP_NS
+#define NABO_TC_SLEEP_NS 2000        // suspend-time hint of the producer's mbarrier waits (0 = plain polling)
 #endif
 #ifndef NABO_TC_UNIFORM_HIT
 #define NABO_TC_UNIFORM_HIT 0
@@ -144,6 +152,8 @@ pack_kernel(const double* __restrict__ x, int ld, int n, int g, int kp, const do
         if (nn > 0.0 && isfinite(nn)) mul = sc / nn; else { mul = 0.0; dead = true; }
     }
     if (live && !IS_QUERY && mask && mask[row]) dead = true;
+    if (!live && !IS_QUERY) dead = true;        // padding rows of the last reference tile: score 60000, like a masked
+                                                // cell, so the epilogue needs no column-limit test
     const double* p = x + (live ? row : 0) * (long long)ld;
     double n2 = 0.0;            // ||x~||^2 of the split value actually fed to the tensor core (scaled units)
     const int nchunks = kp / 8;
@@ -170,7 +180,7 @@ pack_kernel(const double* __restrict__ x, int ld, int n, int g, int kp, const do
             }
             h[e] = v;
         }
-        if (!IS_QUERY && live && 3 * g + 3 > kc * 8 && 3 * g < kc * 8 + 8) {
+        if (!IS_QUERY && (live || dead) && 3 * g + 3 > kc * 8 && 3 * g < kc * 8 + 8) {
             // norm pieces n1 + n2 + n3 = ||r~||^2 (n2 is complete here: columns >= 3g come after segment 0)
             double rem = dead ? 60000.0 : n2;
             for (int t = 0; t < 3; ++t) {
@@ -285,6 +295,9 @@ struct Params {
     const uint32_t* perm_q; // packed query row -> input row (NULL = identity)
     const uint32_t* perm_r; // packed reference row -> input row (NULL = identity)
     const int* item_start;  // first reference tile of every item's sweep (NULL = 0; unsplit kernel only)
+    // balanced last wave (MODE 2): the first n_full items run whole, one per CTA and round; the remaining bal_rem
+    // items are cut into reference pieces so that all CTAs finish together (see work_piece below)
+    int n_full, bal_rem, bal_share, bal_p;      // bal_p > 0: bal_p aligned pieces per item; 0: contiguous ranges
     int dbg;                // NABO_TC_DBG bit mask for timing experiments (0 in production): 1 = skip the final emit
     size_t a_off, b_off, sort_off, bar_off;
 };
@@ -321,16 +334,11 @@ __device__ unsigned long long g_tc_stats[12];  // [2] lanes with a hit, [3] keys
 #endif
 
 // 32 freshly loaded scores of one query: reduce with FMNMX3 and append the ones below tau
-__device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid_cols, uint32_t col0, float tau,
+__device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], uint32_t col0, float tau,
                                              unsigned long long* mybuf, int& cnt TC_ARG) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vr[i]);
-    if (valid_cols < 32) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i >= valid_cols) v[i] = CUDART_INF_F;
-    }
     float g4[4];
 #pragma unroll
     for (int gi = 0; gi < 4; ++gi) {
@@ -385,31 +393,88 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&vr)[32], int valid
 #endif
 }
 
-// work item w -> (query item, first / last reference tile of its range)
-// The unsplit kernel sweeps all reference tiles cyclically from the item's start tile: sweep position jj in
-// [j0, j1) is tile sweep_tile(jj) (start = 0 and no wrap in the split kernel).
-template <bool SPLIT>
-__device__ __forceinline__ void decode_item(const Params& p, int w, int& qitem, int& seg, int& j0, int& j1, int& start) {
+// Work enumeration.  MODE 0: one work item per query item (whole reference sweep, cyclic from the item's start
+// tile).  MODE 1: few items - every item's reference range is cut into n_split equal pieces, each a work item.
+// MODE 2: more items than CTAs and a last wave that would leave SMs idle - the first n_full (a multiple of the grid)
+// items run whole, the other bal_rem items are cut so that every CTA gets the same number of reference tiles:
+//   bal_p > 0 (last wave less than half full): bal_p aligned pieces per item, piece s = tiles [s share, (s+1) share);
+//   bal_p = 0: the tail is one sequence of bal_rem * n_rtiles tiles, CTA c takes [c share, (c+1) share) - up to two
+//              pieces (end of one item, start of the next); an item is cut into at most three pieces.
+// Every piece has its own buffer `slot`, K' list and threshold (segment `seg` of its item); the re-rank takes the
+// union of the lists and the smallest threshold.  Returns false when CTA `c` has no r-th work item.
+template <int MODE>
+__device__ __forceinline__ bool work_piece(const Params& p, int c, int r, int& slot, int& qitem, int& seg, int& j0,
+                                           int& j1, int& start) {
     start = 0;
-    if (!SPLIT) {                      // one piece: the instantiation the large-N path runs is the unsplit kernel
-        qitem = w; seg = 0; j0 = 0; j1 = p.n_rtiles;
-        if (p.item_start) start = p.item_start[w];
-        return;
+    if (MODE == 0) {
+        slot = c + r * (int)gridDim.x;
+        if (slot >= p.n_items) return false;
+        qitem = slot; seg = 0; j0 = 0; j1 = p.n_rtiles;
+        if (p.item_start) start = p.item_start[slot];
+        return true;
     }
-    qitem = w / p.n_split;
-    seg = w - qitem * p.n_split;
-    j0 = (int)((long long)p.n_rtiles * seg / p.n_split);
-    j1 = (int)((long long)p.n_rtiles * (seg + 1) / p.n_split);
+    if (MODE == 1) {
+        slot = c + r * (int)gridDim.x;
+        if (slot >= p.n_items * p.n_split) return false;
+        qitem = slot / p.n_split;
+        seg = slot - qitem * p.n_split;
+        j0 = (int)((long long)p.n_rtiles * seg / p.n_split);
+        j1 = (int)((long long)p.n_rtiles * (seg + 1) / p.n_split);
+        return true;
+    }
+    const int rounds_full = p.n_full / (int)gridDim.x;
+    if (r < rounds_full) {
+        slot = c + r * (int)gridDim.x;
+        qitem = slot; seg = 0; j0 = 0; j1 = p.n_rtiles;
+        return true;
+    }
+    const int tr = r - rounds_full;                     // 0 or 1: piece of the tail
+    if (p.bal_p > 0) {
+        if (tr > 0 || c >= p.bal_rem * p.bal_p) return false;
+        const int i = c / p.bal_p;
+        seg = c - i * p.bal_p;
+        j0 = seg * p.bal_share;
+        j1 = min(p.n_rtiles, j0 + p.bal_share);
+        if (j0 >= j1) return false;
+        qitem = p.n_full + i;
+        slot = p.n_full + i * NABO_TC_MAX_SPLIT + seg;
+        return true;
+    }
+    if (tr > 1) return false;
+    const long long total = (long long)p.bal_rem * p.n_rtiles;
+    const long long lo = (long long)c * p.bal_share, hi = min(total, lo + p.bal_share);
+    if (lo >= hi) return false;
+    int i = (int)(lo / p.n_rtiles);
+    long long a = lo, b = min(hi, (long long)(i + 1) * p.n_rtiles);
+    if (tr == 1) {
+        if (b >= hi) return false;                      // the range does not reach into the next item
+        ++i; a = b; b = hi;
+    }
+    qitem = p.n_full + i;
+    seg = c - (int)(((long long)i * p.n_rtiles) / p.bal_share);
+    j0 = (int)(a - (long long)i * p.n_rtiles);
+    j1 = (int)(b - (long long)i * p.n_rtiles);
+    slot = p.n_full + i * NABO_TC_MAX_SPLIT + seg;
+    return true;
+}
+// number of pieces item i of the tail is cut into (MODE 2)
+__device__ __forceinline__ int tail_pieces(const Params& p, int i) {
+    if (p.bal_p > 0) {
+        int n = 0;
+        for (int s_ = 0; s_ < p.bal_p; ++s_) n += (s_ * p.bal_share < p.n_rtiles) ? 1 : 0;
+        return n;
+    }
+    const long long first = ((long long)i * p.n_rtiles) / p.bal_share;
+    const long long last = ((long long)(i + 1) * p.n_rtiles - 1) / p.bal_share;
+    return (int)(last - first + 1);
 }
 __device__ __forceinline__ int sweep_tile(int jj, int start, int n_rtiles) {
     const int j = jj + start;
     return j >= n_rtiles ? j - n_rtiles : j;
 }
 
-template <int KSTEPS, bool SPLIT>   // K steps of 16 known at compile time (0 = runtime loop); SPLIT: n_split > 1
+template <int KSTEPS, int MODE>   // K steps of 16 known at compile time (0 = runtime loop); MODE: see work_piece
 __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p) {
-    const int n_work = SPLIT ? p.n_items * p.n_split : p.n_items;
-    const int n_seg = SPLIT ? p.n_split : 1;
     extern __shared__ __align__(1024) uint8_t smem[];
     Barriers* bars = reinterpret_cast<Barriers*>(smem + p.bar_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -434,10 +499,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t t = 0, it = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-                int item, seg, j0, j1, start;
-                decode_item<SPLIT>(p, w, item, seg, j0, j1, start);
-                ptx::mbar_wait(&bars->a_empty, (it & 1) ^ 1);
+            for (int wr = 0;; ++wr, ++it) {
+                int w, item, seg, j0, j1, start;
+                if (!work_piece<MODE>(p, blockIdx.x, wr, w, item, seg, j0, j1, start)) break;
+                ptx::mbar_wait_hint(&bars->a_empty, (it & 1) ^ 1, NABO_TC_SLEEP_NS);
                 ptx::mbar_arrive_expect_tx(&bars->a_full, NQ * a_tile_bytes);
                 for (int q = 0; q < NQ; ++q) {
                     const char* src = reinterpret_cast<const char*>(p.qa) + (size_t)(item * NQ + q) * a_tile_bytes;
@@ -447,7 +512,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                 }
                 for (int j = j0; j < j1; ++j, ++t) {
                     const uint32_t s = t % p.stages, use = t / p.stages;
-                    ptx::mbar_wait(&bars->b_empty[s], (use & 1) ^ 1);
+                    ptx::mbar_wait_hint(&bars->b_empty[s], (use & 1) ^ 1, NABO_TC_SLEEP_NS);   // far ahead of the consumers
                     ptx::mbar_arrive_expect_tx(&bars->b_full[s], a_tile_bytes);
                     const char* src = reinterpret_cast<const char*>(p.rb) + (size_t)sweep_tile(j, start, p.n_rtiles) * a_tile_bytes;
                     char* dst = reinterpret_cast<char*>(smem + p.b_off) + (size_t)s * a_tile_bytes;
@@ -471,9 +536,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
             const uint64_t ad0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.a_off), lbo, sbo);
             const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off), lbo, sbo);
             uint32_t t = 0, it = 0, n = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-                int item, seg, j0, j1, start;
-                decode_item<SPLIT>(p, w, item, seg, j0, j1, start);
+            for (int wr = 0;; ++wr, ++it) {
+                int w, item, seg, j0, j1, start;
+                if (!work_piece<MODE>(p, blockIdx.x, wr, w, item, seg, j0, j1, start)) break;
                 ptx::mbar_wait(&bars->a_full, it & 1);
                 for (int j = j0; j < j1; ++j, ++t) {
                     const uint32_t s = t % p.stages, use = t / p.stages;
@@ -524,9 +589,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
             const uint64_t ad0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.a_off) + q * a_tile_bytes, lbo, sbo);
             const uint64_t bd0 = ptx::make_smem_desc(ptx::smem_u32(smem + p.b_off), lbo, sbo);
             uint32_t t = 0, it = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-                int item, seg, j0, j1, start;
-                decode_item<SPLIT>(p, w, item, seg, j0, j1, start);
+            for (int wr = 0;; ++wr, ++it) {
+                int w, item, seg, j0, j1, start;
+                if (!work_piece<MODE>(p, blockIdx.x, wr, w, item, seg, j0, j1, start)) break;
                 ptx::mbar_wait(&bars->a_full, it & 1);
                 for (int j = j0; j < j1; ++j, ++t) {
                     const uint32_t s = t % p.stages, use = t / p.stages;
@@ -565,9 +630,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
         uint32_t t = 0;
         uint32_t* hist = reinterpret_cast<uint32_t*>(smem + p.sort_off) + (size_t)warp * 256;
         TC_DECL;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            int item, seg, j0, j1, start;
-            decode_item<SPLIT>(p, w, item, seg, j0, j1, start);
+        for (int wr = 0;; ++wr) {
+            int w, item, seg, j0, j1, start;
+            if (!work_piece<MODE>(p, blockIdx.x, wr, w, item, seg, j0, j1, start)) break;
             unsigned long long* mybuf = p.cand_buf + ((size_t)w * NQ * TILE + slot) * CAP;
 #ifdef NABO_TC_DBG_NOHIT
             float tau = -CUDART_INF_F;              // timing experiment: nothing is ever appended (results invalid)
@@ -589,7 +654,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                 TC_CLK_ADD(7, t_w);
                 const int jt = sweep_tile(j, start, p.n_rtiles);  // the reference tile this sweep position holds
                 NABO_DEV_ASSERT(jt >= 0 && jt < p.n_rtiles);
-                const int col_limit = p.n_ref - jt * TILE;       // columns >= col_limit are padding
                 // the compaction of every lane whose buffer passed `lim` (soft limit once per tile, after the
                 // accumulator has been handed back; hard limit otherwise: the next chunk may append 32 more)
                 auto compact_over = [&](int lim) {
@@ -603,7 +667,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                         const int n = __shfl_sync(0xffffffffu, cnt, src);
                         int nc;
                         float nt;
-                        compact_select(gb, n, lane, p.kprime, p.soft - 8, hist, nc, nt);
+                        compact_select<KPL>(gb, n, lane, p.kprime, p.soft - 8, hist, nc, nt);
                         if (lane == src) { cnt = nc; tau = nt; }
                         if (lane == 0) TC_STAT(4, 1);
                     }
@@ -622,12 +686,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
 #pragma unroll 1
                 for (int c = 0; c < TILE / CHUNK; c += 2) {
                     ptx::tmem_ld_32x32(taddr0 + (c + 1) * CHUNK, vb);
-                    filter_chunk(va, col_limit - c * CHUNK, (uint32_t)(jt * TILE + c * CHUNK), tau, mybuf, cnt TC_PASS);
+                    filter_chunk(va, (uint32_t)(jt * TILE + c * CHUNK), tau, mybuf, cnt TC_PASS);
                     compact_over(CAP - CHUNK);
                     ptx::tmem_ld_wait();
                     if (c + 2 < TILE / CHUNK) ptx::tmem_ld_32x32(taddr0 + (c + 2) * CHUNK, va);
                     else release_acc();
-                    filter_chunk(vb, col_limit - (c + 1) * CHUNK, (uint32_t)(jt * TILE + (c + 1) * CHUNK), tau, mybuf, cnt TC_PASS);
+                    filter_chunk(vb, (uint32_t)(jt * TILE + (c + 1) * CHUNK), tau, mybuf, cnt TC_PASS);
                     compact_over(c + 2 < TILE / CHUNK ? CAP - CHUNK : p.soft);
                     if (c + 2 < TILE / CHUNK) ptx::tmem_ld_wait();
                 }
@@ -641,7 +705,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
                     TC_CLK_ADD(8, t_l);
                     if (c == TILE / CHUNK - 1) release_acc();
                     TC_CLK(t_f);
-                    filter_chunk(vr, col_limit - c * CHUNK, (uint32_t)(jt * TILE + c * CHUNK), tau, mybuf, cnt TC_PASS);
+                    filter_chunk(vr, (uint32_t)(jt * TILE + c * CHUNK), tau, mybuf, cnt TC_PASS);
                     TC_CLK_ADD(6, t_f);
                     compact_over(c == TILE / CHUNK - 1 ? p.soft : CAP - CHUNK);
                 }
@@ -665,33 +729,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
 // Final selection: one warp per (query, reference range).  Sorts the buffer the sweep left behind, emits the K'
 // best as reference rows of the INPUT order (perm_r) into the query's INPUT row (perm_q) and the threshold every
 // other reference of the range is at or above.
+template <int MODE, bool PERM>     // PERM: operands were packed in locality order (perm_q / perm_r map back to input rows)
 __global__ void __launch_bounds__(256)
-emit_kernel(const Params p, int n_work, int n_seg) {
+emit_kernel(const Params p, int n_slots_items, int n_seg) {
     const int lane = threadIdx.x & 31;
-    const long long wq = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);          // (work item, slot)
-    if (wq >= (long long)n_work * NQ * TILE) return;
+    const long long wq = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);          // (buffer slot, query of the item)
+    if (wq >= (long long)n_slots_items * NQ * TILE) return;
     const int w = (int)(wq / (NQ * TILE)), slot = (int)(wq - (long long)w * NQ * TILE);
-    const int item = n_seg > 1 ? w / n_seg : w, seg = n_seg > 1 ? w - item * n_seg : 0;
+    int item, seg = 0, n_empty_after = 0;       // n_empty_after: segments of this query that hold nothing (MODE 2)
+    bool exists = true;
+    if (MODE == 0) {
+        item = w;
+    } else if (MODE == 1) {
+        item = w / n_seg;
+        seg = w - item * n_seg;
+    } else if (w < p.n_full) {
+        item = w;
+        n_empty_after = n_seg - 1;               // a whole item: segments 1.. stay empty
+    } else {
+        const int t = w - p.n_full, i = t / NABO_TC_MAX_SPLIT;
+        seg = t - i * NABO_TC_MAX_SPLIT;
+        item = p.n_full + i;
+        exists = seg < tail_pieces(p, i);
+    }
     const long long qp = (long long)item * NQ * TILE + slot;                       // packed position
-    if (qp >= p.n_query) return;
+    if (qp >= p.n_query || seg >= n_seg) return;
+    const long long qg = PERM ? (long long)p.perm_q[qp] : qp;                     // input row
+    if (!exists) {                               // no such piece: an empty list that rejected nothing
+        for (int i = lane; i < p.kc_out; i += 32) p.cand_idx[(qg * n_seg + seg) * p.kc_out + i] = -1;
+        if (lane == 0) p.cert_tau[(long long)seg * p.n_query + qg] = CUDART_INF_F;
+        return;
+    }
     const int n = p.cand_cnt[wq];
     const float old_tau = p.cand_tau[wq];
     NABO_DEV_ASSERT(n >= 0 && n <= CAP);
-    uint32_t ks[4], kpl[4];
+    uint32_t ks[KPL], kpl[KPL];
     int nc;
     float nt;
-    compact_sort_inline(p.cand_buf + (size_t)wq * CAP, n, lane, p.kprime, ks, kpl, nc, nt);
-    const long long qg = p.perm_q ? (long long)p.perm_q[qp] : qp;                 // input row
+    compact_sort_inline<KPL>(p.cand_buf + (size_t)wq * CAP, n, lane, p.kprime, ks, kpl, nc, nt);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 4; ++u) {                 // kc_out <= 128
         const int i = u * 32 + lane;
         if (i < p.kc_out) {
             int32_t id = -1;
-            if (i < nc) id = p.perm_r ? (int32_t)p.perm_r[kpl[u]] : (int32_t)kpl[u];
+            if (i < nc && kpl[u] < (uint32_t)p.n_ref) id = PERM ? (int32_t)p.perm_r[kpl[u]] : (int32_t)kpl[u];
             p.cand_idx[(qg * n_seg + seg) * p.kc_out + i] = id;
         }
     }
     if (lane == 0) p.cert_tau[(long long)seg * p.n_query + qg] = n >= p.kprime ? nt : old_tau;
+    for (int e = 1; e <= n_empty_after; ++e) {
+        for (int i = lane; i < p.kc_out; i += 32) p.cand_idx[(qg * n_seg + e) * p.kc_out + i] = -1;
+        if (lane == 0) p.cert_tau[(long long)e * p.n_query + qg] = CUDART_INF_F;
+    }
 }
 
 }  // namespace tc
@@ -702,7 +791,7 @@ bool nabo_tc_supported(int g, int k, int drop_first) {
     const int kp = tc::kp_for(g);
     const tc::SmemPlan pl = tc::plan_smem(kp);
     const int ksel = k + (drop_first ? 1 : 0);
-    return pl.stages >= 2 && ksel + 8 <= tc::CAP - tc::CHUNK;
+    return pl.stages >= 2 && ksel + 8 <= tc::MAX_KPRIME;
 }
 
 int nabo_tc_kprime(int k, int drop_first) {
@@ -711,7 +800,7 @@ int nabo_tc_kprime(int k, int drop_first) {
     // (provable, 2^-16) score error bound; measured at 100k x 100k / 200k x 1.25M, k = 30: +4 ranks ->
     // 76 / 944 uncertified rows, +6 -> 0 / 12, +8 -> 0 / 0, while the kernel time barely moves.
     int kprime = ksel + (ksel / 4 > 8 ? ksel / 4 : 8);
-    if (kprime > tc::CAP - tc::CHUNK) kprime = tc::CAP - tc::CHUNK;
+    if (kprime > tc::MAX_KPRIME) kprime = tc::MAX_KPRIME;
     return kprime;
 }
 
@@ -723,6 +812,19 @@ static bool nabo_tc_order_enabled() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("NABO_TC_ORDER");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
+}
+
+// NABO_TC_BALANCE=1 switches the balanced last wave (MODE 2) on.  Measured on B200 (tools/probe_fast.py): correct
+// (tests/test_gpu_tc.py::test_balanced_last_wave_equals_exact) but not a gain - at 100 k x 100 k the pieces start with
+// a cold threshold (candidate kernel 3.79 -> 4.24 ms) and the re-rank walks three K' lists per query (0.87 -> 1.43 ms);
+// at 200 k x 1.25 M the kernel gains 3 % and the re-rank loses as much.  Off by default.
+static bool nabo_tc_balance_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NABO_TC_BALANCE");
         v = (e && e[0] == '1') ? 1 : 0;
     }
     return v != 0;
@@ -788,9 +890,13 @@ size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_fi
 // Runs norms -> scale -> pack -> candidate kernel.  Outputs (device, inside the arena):
 // cand_idx [n_query][kprime], cert_tau [n_query], qn2 [n_query], scal[4].
 int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
-                       int metric, const uint8_t* mask, int drop_first, int n_split, NaboArena& ar, int32_t** cand_idx_out,
+                       int metric, const uint8_t* mask, int drop_first, int* n_split_io, NaboArena& ar, int32_t** cand_idx_out,
                        int* kprime_out, float** cert_tau_out, double** qn2_out, double** scal_out, int* launches,
                        NaboStageTimer& tm, cudaStream_t st) {
+    // *n_split_io in: reference pieces per item when there are few items (nabo_tc_split), or 0 = one piece and no
+    // balancing of the last wave (the public candidate entry point: one K' list per query); out: K' lists per query
+    int n_split = *n_split_io;
+    const bool may_balance = n_split >= 1;
     const int kp = tc::kp_for(g);
     const tc::SmemPlan pl = tc::plan_smem(kp);
     const size_t tb = tc::tile_bytes(kp);
@@ -800,24 +906,43 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     const int kprime = nabo_tc_kprime(k, drop_first);
     if (n_split < 1 || n_split > NABO_TC_MAX_SPLIT) n_split = 1;
     const int grid = tc_grid(n_items * n_split);
+    // MODE 2 (see work_piece): more items than CTAs, a last wave between 5 % and 90 % full, room for three K' lists
+    int mode = n_split > 1 ? 1 : 0, n_full = n_items, bal_rem = 0, bal_share = 0, bal_p = 0;
+    if (mode == 0 && may_balance && n_items > grid && 3 * kprime <= 128 && n_rtiles >= 96 && nabo_tc_balance_enabled()) {
+        const int rem = n_items % grid;
+        if (rem > 0 && rem * 20 >= grid && rem * 10 <= grid * 9) {
+            mode = 2;
+            n_full = n_items - rem;
+            bal_rem = rem;
+            if (rem * 2 >= grid) {                       // contiguous ranges, <= 3 pieces per item
+                bal_p = 0;
+                bal_share = (int)(((long long)rem * n_rtiles + grid - 1) / grid);
+            } else {                                     // aligned pieces
+                bal_p = grid / rem < NABO_TC_MAX_SPLIT ? grid / rem : NABO_TC_MAX_SPLIT;
+                bal_share = (n_rtiles + bal_p - 1) / bal_p;
+            }
+        }
+    }
+    const int n_seg = mode == 2 ? NABO_TC_MAX_SPLIT : n_split;
+    const int n_slot_items = mode == 2 ? n_full + bal_rem * NABO_TC_MAX_SPLIT : n_items * n_split;
 
     __half* qa = (__half*)ar.take<char>((size_t)n_qtiles * tb);
     __half* rb = (__half*)ar.take<char>((size_t)n_rtiles * tb);
     double* qnorm = ar.take<double>(n_query);
     double* qn2 = ar.take<double>(n_query);
     double* rnorm = ar.take<double>(n_ref);
-    const size_t n_slots = (size_t)n_items * n_split * tc::NQ * tc::TILE;
+    const size_t n_slots = (size_t)n_slot_items * tc::NQ * tc::TILE;
     unsigned long long* cbuf = ar.take<unsigned long long>(n_slots * tc::CAP);
     int* ccnt = ar.take<int>(n_slots);
     float* ctau = ar.take<float>(n_slots);
-    int32_t* cand = ar.take<int32_t>((size_t)n_query * kprime * n_split);
-    float* tau = ar.take<float>((size_t)n_query * n_split);
+    int32_t* cand = ar.take<int32_t>((size_t)n_query * kprime * n_seg);
+    float* tau = ar.take<float>((size_t)n_query * n_seg);
     double* scal = ar.take<double>(4);
     unsigned int* maxbits = ar.take<unsigned int>(2);
     if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small for the tensor-core pass");
 
     // locality order (see order kernels above): only worth its ~10 small launches on a real sweep
-    const bool ordered = n_split == 1 && n_rtiles >= 64 && nabo_tc_order_enabled();
+    const bool ordered = mode == 0 && n_rtiles >= 64 && nabo_tc_order_enabled();
     uint32_t *perm_q = nullptr, *perm_r = nullptr;
     int* item_start = nullptr;
     if (ordered) {
@@ -863,6 +988,7 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     p.qa = qa; p.rb = rb;
     p.n_query = n_query; p.n_ref = n_ref; p.kp = kp; p.n_items = n_items; p.n_rtiles = n_rtiles;
     p.stages = pl.stages; p.kprime = kprime; p.kc_out = kprime; p.n_split = n_split;
+    p.n_full = n_full; p.bal_rem = bal_rem; p.bal_share = bal_share; p.bal_p = bal_p;
     p.cand_buf = cbuf; p.cand_cnt = ccnt; p.cand_tau = ctau; p.cand_idx = cand; p.cert_tau = tau;
     p.perm_q = perm_q; p.perm_r = perm_r; p.item_start = item_start;
     {
@@ -871,32 +997,38 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     }
     p.a_off = pl.a_off; p.b_off = pl.b_off; p.sort_off = pl.sort_off; p.bar_off = pl.bar_off;
     p.soft = tc::CAP - tc::CHUNK - 16 > kprime ? tc::CAP - tc::CHUNK - 16 : kprime;
-#define NABO_TC_LAUNCH(KS)                                                                                          \
+#define NABO_TC_LAUNCH1(KS, MD)                                                                                    \
     do {                                                                                                           \
-        if (n_split > 1) {                                                                                         \
-            NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel<KS, true>,                                        \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));           \
-            tc::candidates_kernel<KS, true><<<grid, tc::NTHREADS, pl.total, st>>>(p);                              \
-        } else {                                                                                                   \
-            NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel<KS, false>,                                       \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));           \
-            tc::candidates_kernel<KS, false><<<grid, tc::NTHREADS, pl.total, st>>>(p);                             \
-        }                                                                                                          \
+        NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel<KS, MD>,                                              \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));               \
+        tc::candidates_kernel<KS, MD><<<grid, tc::NTHREADS, pl.total, st>>>(p);                                    \
+    } while (0)
+#define NABO_TC_LAUNCH(KS)                                                                                         \
+    do {                                                                                                           \
+        if (mode == 1) NABO_TC_LAUNCH1(KS, 1);                                                                     \
+        else if (mode == 2) NABO_TC_LAUNCH1(KS, 2);                                                                \
+        else NABO_TC_LAUNCH1(KS, 0);                                                                               \
     } while (0)
     if (kp == 160) NABO_TC_LAUNCH(10);        // g = 50 (BASELINE configs 2-5)
     else if (kp == 80) NABO_TC_LAUNCH(5);     // g = 25 (config 1)
     else NABO_TC_LAUNCH(0);
+#undef NABO_TC_LAUNCH1
 #undef NABO_TC_LAUNCH
     NABO_LAUNCH_CHECK("candidates_kernel");
     tm.end(0);             // the final selection below is timed with the re-rank stage
-    tc::emit_kernel<<<(unsigned)((n_slots + 7) / 8), 256, 0, st>>>(p, n_items * n_split, n_split);
+    const unsigned egrid = (unsigned)((n_slots + 7) / 8);
+    if (mode == 0 && perm_q) tc::emit_kernel<0, true><<<egrid, 256, 0, st>>>(p, n_slot_items, n_seg);
+    else if (mode == 0) tc::emit_kernel<0, false><<<egrid, 256, 0, st>>>(p, n_slot_items, n_seg);
+    else if (mode == 1) tc::emit_kernel<1, false><<<egrid, 256, 0, st>>>(p, n_slot_items, n_seg);
+    else tc::emit_kernel<2, false><<<egrid, 256, 0, st>>>(p, n_slot_items, n_seg);
     NABO_LAUNCH_CHECK("emit_kernel");
     *launches += 1;
-    if (n_split > 1) {
-        int rc = nabo_tau_min_launch(tau, n_query, n_split, st);
+    if (n_seg > 1) {
+        int rc = nabo_tau_min_launch(tau, n_query, n_seg, st);
         if (rc) return rc;
         *launches += 1;
     }
+    *n_split_io = n_seg;
     *cand_idx_out = cand; *kprime_out = kprime; *cert_tau_out = tau; *qn2_out = qn2; *scal_out = scal;
     *launches += 6;
     return 0;
@@ -934,8 +1066,9 @@ extern "C" int nabo_knn_candidates(const double* q, int ldq, const double* r, in
     float* tau = nullptr;
     double *qn2 = nullptr, *scal = nullptr;
     int kprime = 0, launches = 0;
-    int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, ref_mask, drop_first, 1, ar, &cand, &kprime,
-                                &tau, &qn2, &scal, &launches, tm, st);
+    int one_list = 0;
+    int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, ref_mask, drop_first, &one_list, ar, &cand,
+                                &kprime, &tau, &qn2, &scal, &launches, tm, st);
     if (rc) return rc;
     NABO_CUDA(cudaMemcpyAsync(out_cand, cand, sizeof(int32_t) * (size_t)n_query * kprime, cudaMemcpyDeviceToDevice, st));
     NABO_CUDA(cudaMemcpyAsync(out_tau, tau, sizeof(float) * (size_t)n_query, cudaMemcpyDeviceToDevice, st));
