@@ -62,7 +62,9 @@ def parse():
     ap.add_argument("--no-projection", action="store_true", help="skip the projection (A1/A2) measurement")
     ap.add_argument("--no-ref-sharded", action="store_true", help="skip the reference-sharded (config 4) block")
     ap.add_argument("--ref-rows-per-gpu", type=int, default=1_250_000)
-    ap.add_argument("--ref-batch", type=int, default=200_000, help="targets per step of the reference-sharded block")
+    ap.add_argument("--ref-batch", type=int, default=227_328,
+                    help="targets per step of the reference-sharded block (default 4 x 148 SMs x 384 queries per work item: "
+                         "whole waves of the persistent candidate kernel; 5 batches = 1.14 M targets)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the modified-Canberra measurement")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per cpu_baseline sample")
     return ap.parse_args()
@@ -763,7 +765,7 @@ def run_b200(a):
             line["mod_canberra"]["roofline"]["traffic_source"] = roof.get("traffic_source")
 
     if not a.no_ref_sharded and a.metric == "euclidean" and a.engine == "fast":
-        # BASELINE config 4 under the same clock: world x 1.25 M reference rows, 5 batches of 200 k targets
+        # BASELINE config 4 under the same clock: world x 1.25 M reference rows, 5 batches of --ref-batch targets
         line["ref_sharded"] = ref_sharded_block(a, dev, rank, world, a.ref_rows_per_gpu, a.ref_batch, 5,
                                                 max(5, a.steps // 2), 2)
         line["score_determinism"] = score_determinism_check(dev, rank, world, ref, ref_knn, k)
