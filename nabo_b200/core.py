@@ -652,7 +652,8 @@ _PIPE: Dict[tuple, _HostPipeline] = {}
 
 
 def map_cells_host(target_host: torch.Tensor, ref, ref_knn, k: int, metric: Optional[str] = None,
-                   dist_factor: float = 0.25, ref_mask=None, mode: str = "fast", chunks: int = 2) -> Dict[str, torch.Tensor]:
+                   dist_factor: float = 0.25, ref_mask=None, mode: str = "fast", chunks: int = 2,
+                   min_piece: int = 32768) -> Dict[str, torch.Tensor]:
     """Host-buffer form of ``map_cells``: ``target_host`` is a pinned CPU float64 (N, g) tensor; the results
     land in pinned host tensors (idx, dist, weights, scores).  The targets are processed in ``chunks``
     pieces so that the host->device copy of piece i+1 and the device->host copy of piece i-1 overlap the
@@ -670,7 +671,7 @@ def map_cells_host(target_host: torch.Tensor, ref, ref_knn, k: int, metric: Opti
         pipe = _PIPE[key] = _HostPipeline(n, g, int(k), m, rd.device)
     met = resolve_metric(metric, False)
     comp = torch.cuda.current_stream()
-    chunks = max(1, min(int(chunks), n // 32768 if n >= 65536 else 1))
+    chunks = max(1, min(int(chunks), n // int(min_piece) if n >= 2 * int(min_piece) else 1))
     bounds = [n * i // chunks for i in range(chunks + 1)]
     pipe.s_in.wait_stream(comp)
     pipe.s_out.wait_stream(comp)
