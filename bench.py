@@ -313,6 +313,7 @@ def ref_sharded_block(a, dev, rank, world, rows_per_gpu, n_batch, n_batches, ste
         stage_ms["knn_rerank"] = sum(x["rerank_ms"] for x in kstats) / len(kstats)
         stage_ms["knn_prepare"] = sum(x["prep_ms"] for x in kstats) / len(kstats)
         stage_ms["knn_exact_fallback"] = sum(x["fallback_ms"] for x in kstats) / len(kstats)
+        stage_ms["knn_rows_to_exact_fallback"] = sum(x["rows_exact_fallback"] for x in kstats) / len(kstats)
     st = torch.tensor([stage_ms.get(n_, 0.0) for n_ in sorted(stage_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(st, op=dist.ReduceOp.MAX)

@@ -247,7 +247,7 @@ knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict
     const int nq_total = n_rows_dev ? *n_rows_dev : n_query;   // fallback mode: row list on device
     // fallback for FEW rows: the reference range is split over blockIdx.y and the partial lists are
     // merged afterwards (mode 1); with many rows the plain row-parallel kernel is used (mode 2)
-    if (sp.mode == 1 && nq_total > sp.f_max) return;
+    if (sp.mode == 1 && (nq_total > sp.f_max || nq_total <= sp.f_min)) return;
     if (sp.mode == 2 && nq_total <= sp.f_max) return;
     const int r_lo = sp.mode == 1 ? (int)((long long)n_ref * blockIdx.y / sp.nsplit) / TR * TR : 0;
     const int r_hi = sp.mode == 1 ? (blockIdx.y + 1 == (unsigned)sp.nsplit
@@ -403,7 +403,7 @@ fallback_merge_kernel(const NaboExactSplit sp, const int* __restrict__ row_ids, 
                       int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const NaboRoute route) {
     extern __shared__ double smem[];
     const int n_rows = *n_rows_dev;
-    if (n_rows > sp.f_max) return;
+    if (n_rows > sp.f_max || n_rows <= sp.f_min) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x * 4 + warp;
     if (qi >= n_rows) return;
@@ -446,13 +446,77 @@ fallback_merge_kernel(const NaboExactSplit sp, const int* __restrict__ row_ids, 
     }
 }
 
+// the same merge for the few-rows split (up to NABO_FALLBACK_FEW_ENTRIES partial entries per row): one block per row,
+// block-wide bitonic sort in shared memory
+__global__ void __launch_bounds__(256)
+fallback_merge_few_kernel(const NaboExactSplit sp, const int* __restrict__ row_ids, const int* __restrict__ n_rows_dev,
+                          int k, int drop_first, int idx_offset, const uint8_t* __restrict__ mask, int capp,
+                          int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const NaboRoute route) {
+    extern __shared__ double smem[];
+    const int n_rows = *n_rows_dev;
+    if (n_rows > sp.f_max || n_rows <= sp.f_min) return;
+    const int qi = blockIdx.x;
+    if (qi >= n_rows) return;
+    const int ksel = k + (drop_first ? 1 : 0);
+    double* d = smem;
+    int* ix = (int*)(smem + capp);
+    __shared__ int s_valid;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    const int tot = sp.nsplit * ksel;
+    int n_valid = 0;
+    for (int c = threadIdx.x; c < capp; c += blockDim.x) {
+        double dv = CUDART_INF;
+        int id = 0x7fffffff;
+        if (c < tot) {
+            const int sidx = c / ksel, j = c - sidx * ksel;
+            const size_t o = ((size_t)sidx * sp.f_max + qi) * ksel + j;
+            const int i0 = sp.part_idx[o];
+            if (i0 >= 0) { id = i0; dv = sp.part_dist[o]; ++n_valid; }
+        }
+        d[c] = dv; ix[c] = id;
+    }
+    atomicAdd(&s_valid, n_valid);
+    __syncthreads();
+    for (int size = 2; size <= capp; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (capp >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const double dl = d[lo], dh = d[hi];
+                const int il = ix[lo], ih = ix[hi];
+                if (up ? nabo_less(dh, ih, dl, il) : nabo_less(dl, il, dh, ih)) { d[lo] = dh; d[hi] = dl; ix[lo] = ih; ix[hi] = il; }
+            }
+            __syncthreads();
+        }
+    const long long orow = row_ids[qi];
+    int32_t* oi;
+    double* od;
+    nabo_route_row(route, orow, k, out_idx, out_dist, oi, od);
+    const int skip = drop_first ? 1 : 0;
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const int src = t + skip;
+        int id = -1;
+        double dv = CUDART_NAN;
+        if (src < s_valid) {
+            id = ix[src];
+            dv = d[src];
+            if (dv == CUDART_INF || (mask && mask[id])) dv = CUDART_NAN;
+            id += idx_offset;
+        }
+        oi[t] = id;
+        od[t] = dv;
+    }
+}
+
 int nabo_exact_split_count(int ksel) {
     int s = 2048 / ksel;
     return s > 48 ? 48 : (s < 1 ? 1 : s);
 }
 size_t nabo_exact_split_workspace(int ksel) {
-    (void)ksel;   // nsplit * ksel <= 2048 for every ksel: one bound, monotone in nothing
-    return (size_t)2048 * NABO_FALLBACK_SPLIT_ROWS * (sizeof(int32_t) + sizeof(double)) + 512;
+    (void)ksel;   // nsplit * ksel <= 2048 for every ksel: one bound, monotone in nothing; + the few-rows region
+    return (size_t)2048 * NABO_FALLBACK_SPLIT_ROWS * (sizeof(int32_t) + sizeof(double)) + 512 +
+           (size_t)NABO_FALLBACK_FEW_ENTRIES * NABO_FALLBACK_FEW_ROWS * (sizeof(int32_t) + sizeof(double)) + 512;
 }
 
 // Exact engine on the rows listed in row_ids[0 .. *n_rows_dev): split over the reference when the rows
@@ -464,10 +528,36 @@ int nabo_knn_exact_fallback(const double* q, int ldq, const double* r, int ldr, 
                             const int* row_ids, const int* n_rows_dev, void* split_ws, int32_t* out_idx,
                             double* out_dist, const NaboRoute& route, cudaStream_t st) {
     const int ksel = k + (drop_first ? 1 : 0);
+    // (a) a handful of rows against a large reference: two pieces per SM, block-wide merge
+    const bool few = n_ref >= NABO_FALLBACK_FEW_MIN_REF;
+    if (few) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        NaboExactSplit sf;
+        sf.mode = 1;
+        sf.nsplit = NABO_FALLBACK_FEW_ENTRIES / ksel < 2 * sms ? NABO_FALLBACK_FEW_ENTRIES / ksel : 2 * sms;
+        sf.f_max = NABO_FALLBACK_FEW_ROWS;
+        sf.f_min = 0;
+        char* base = (char*)split_ws + (size_t)2048 * NABO_FALLBACK_SPLIT_ROWS * (sizeof(int32_t) + sizeof(double)) + 512;
+        sf.part_dist = (double*)base;
+        sf.part_idx = (int32_t*)(sf.part_dist + (size_t)sf.nsplit * sf.f_max * ksel);
+        int rc0 = nabo_knn_exact_launch_ex(q, ldq, r, ldr, NABO_FALLBACK_FEW_ROWS, n_ref, g, ksel, metric, f, mask, 0, 0,
+                                           row_ids, n_rows_dev, sf, out_idx, out_dist, route, st);
+        if (rc0) return rc0;
+        const int cappf = nabo_next_pow2(sf.nsplit * ksel);
+        const size_t smf = (size_t)cappf * (sizeof(double) + sizeof(int));
+        NABO_CUDA(cudaFuncSetAttribute(fallback_merge_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+        fallback_merge_few_kernel<<<NABO_FALLBACK_FEW_ROWS, 256, smf, st>>>(sf, row_ids, n_rows_dev, k, drop_first, idx_offset,
+                                                                         mask, cappf, out_idx, out_dist, route);
+        NABO_LAUNCH_CHECK("fallback_merge_few_kernel");
+    }
+    // (b) up to NABO_FALLBACK_SPLIT_ROWS rows: up to 48 pieces, one warp merges a row
     NaboExactSplit sp;
     sp.mode = 1;
     sp.nsplit = nabo_exact_split_count(ksel);
     sp.f_max = NABO_FALLBACK_SPLIT_ROWS;
+    sp.f_min = few ? NABO_FALLBACK_FEW_ROWS : 0;
     sp.part_dist = (double*)split_ws;
     sp.part_idx = (int32_t*)(sp.part_dist + (size_t)sp.nsplit * sp.f_max * ksel);
     int rc = nabo_knn_exact_launch_ex(q, ldq, r, ldr, NABO_FALLBACK_SPLIT_ROWS, n_ref, g, ksel, metric, f, mask, 0, 0,
@@ -491,7 +581,7 @@ int nabo_knn_exact_launch(const double* q, int ldq, const double* r, int ldr, in
                           const int* row_ids, const int* n_rows_dev, int32_t* out_idx, double* out_dist,
                           const NaboRoute& route, cudaStream_t st) {
     NaboExactSplit sp;
-    sp.mode = 0; sp.nsplit = 1; sp.f_max = 0; sp.part_idx = nullptr; sp.part_dist = nullptr;
+    sp.mode = 0; sp.nsplit = 1; sp.f_max = 0; sp.f_min = 0; sp.part_idx = nullptr; sp.part_dist = nullptr;
     return nabo_knn_exact_launch_ex(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset,
                                     row_ids, n_rows_dev, sp, out_idx, out_dist, route, st);
 }

@@ -32,9 +32,14 @@ __device__ __forceinline__ void nabo_route_row(const NaboRoute& rt, long long ro
 // reference range over blockIdx.y and merges the partial lists (a single block would otherwise scan
 // the whole reference alone and dominate the call).
 #define NABO_FALLBACK_SPLIT_ROWS 2048
+// A handful of uncertified rows against a large reference: the range is cut into many more pieces (two per SM) and
+// the partial lists are merged by a whole block per row - one row at 1.25 M references: 5.2 -> under 1 ms.
+#define NABO_FALLBACK_FEW_ROWS 64
+#define NABO_FALLBACK_FEW_ENTRIES 16384       /* pieces x (k + drop_first) of the few-rows merge */
+#define NABO_FALLBACK_FEW_MIN_REF 262144
 struct NaboExactSplit {
-    int mode;            // 0 = plain, 1 = split partial pass (runs iff rows <= f_max), 2 = plain iff rows > f_max
-    int nsplit, f_max;
+    int mode;            // 0 = plain, 1 = split partial pass (runs iff f_min < rows <= f_max), 2 = plain iff rows > f_max
+    int nsplit, f_max, f_min;
     int32_t* part_idx;   // [nsplit][f_max][ksel]
     double* part_dist;
 };

@@ -298,3 +298,27 @@ def test_balanced_last_wave_equals_exact(core, metric, n, m):
         ei, ed = core.knn(q, r, k, metric, mode="exact", **kw)
         assert torch.equal(fi, ei) and torch.equal(fd.view(torch.int64), ed.view(torch.int64))
         assert st["candidates_per_row"] == 38 and st["rows_exact_fallback"] < n // 100
+
+
+def test_few_uncertified_rows_against_a_large_reference(core):
+    """A handful of rows the certificate cannot clear (NaN coordinate, more exact ties than candidates) against
+    >= 262 144 references take the few-rows split of the exact fallback (two reference pieces per SM, block-wide
+    merge); more rows take the 48-piece split.  Both must return what the exact engine returns."""
+    import torch
+    from nabo_b200 import synth
+    m, g, k = 300_000, 20, 10
+    r = synth.pc_mixture(m, g, seed=1)
+    r[1000:1060] = r[1000]                          # 60 identical cells: a tie class larger than K'
+    for n_bad in (3, 200):
+        q = synth.pc_mixture(3000, g, seed=101)
+        q[9] = r[1000]
+        q[11] = r[1000] + 1e-9
+        bad = np.arange(20, 20 + n_bad)
+        q[bad, 3] = np.nan
+        qd, rd = torch.from_numpy(q).cuda(), torch.from_numpy(r).cuda()
+        for kw in (dict(), dict(drop_first=True, idx_offset=5)):
+            fi, fd, st = core.knn(qd, rd, k, "euclidean", mode="fast", return_stats=True, **kw)
+            ei, ed = core.knn(qd, rd, k, "euclidean", mode="exact", **kw)
+            assert st["rows_exact_fallback"] >= n_bad + 1
+            assert torch.equal(fi, ei)
+            assert same_bits(fd.cpu().numpy(), ed.cpu().numpy())
