@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "knn_internal.cuh"
+#include "select.cuh"
 
 // ------------------------------------------------------------------ error channel
 static thread_local char g_err[512] = "";
@@ -639,13 +640,14 @@ __device__ __forceinline__ double cert_lower_bound(const NaboCert& c, int qi, fl
     return 0.5 * e * e * (1.0 - 1e-9);
 }
 
-template <int METRIC>
+template <int METRIC, bool FROM_BUF>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ r, int ldr, int n_query,
               int n_ref, int g, int k, double f, const uint8_t* __restrict__ mask, int drop_first,
               int idx_offset, const int32_t* __restrict__ cand, int n_cand, int capp, const NaboCert cert,
               int* __restrict__ fail_rows, int* __restrict__ fail_count,
-              int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const NaboRoute route) {
+              int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const NaboRoute route,
+              const NaboCandBuf cb) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x * 4 + warp;
@@ -658,9 +660,37 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
     const double* x = q + (long long)qi * ldq;
     double nq = 0.0;
     if (METRIC == NABO_COSINE) nq = seq_sqnorm(x, g);
+    // FROM_BUF: final K' selection of the query's candidate buffer (what tc::emit_kernel does otherwise): the 128
+    // keys are sorted by score in registers, element u * 32 + lane of the sorted list ends up in kpl[u]
+    uint32_t ks[4], kpl[4];
+    int nc = 0;
+    float tau_q = CUDART_INF_F;
+    if (FROM_BUF) {
+        const int n = cb.cnt[qi];
+        const unsigned long long* gb = cb.buf + (size_t)qi * sel::CAP;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = u * 32 + lane;
+            const unsigned long long kv = i < n ? __ldcg(gb + i) : 0ull;
+            ks[u] = i < n ? float_to_sortable(__uint_as_float((uint32_t)(kv >> 32))) : 0xffffffffu;
+            kpl[u] = (uint32_t)kv;
+        }
+        sel::sortn<4>(ks, kpl, lane);
+        nc = n < cb.kprime ? n : cb.kprime;
+        const int e = cb.kprime - 1;                      // kprime <= 64
+        const uint32_t ts = __shfl_sync(0xffffffffu, (e >> 5) ? ks[1] : ks[0], e & 31);
+        tau_q = n >= cb.kprime ? sortable_to_float(ts) : cb.tau[qi];
+    } else if (cert.kind != NABO_CERT_NONE) {
+        tau_q = cert.tau[qi];
+    }
     int n_valid = 0, n_finite = 0;
-    for (int c = lane; c < capp; c += 32) {
-        int j = c < n_cand ? cand[(long long)qi * n_cand + c] : -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int c = u * 32 + lane;
+        if (u * 32 >= capp) break;
+        int j;
+        if (FROM_BUF) j = (u < 2 && c < nc) ? (int)kpl[u] : -1;
+        else j = c < n_cand ? cand[(long long)qi * n_cand + c] : -1;
         double key = CUDART_INF;
         int id = 0x7fffffff;
         if (j >= 0 && j < n_ref) {
@@ -700,7 +730,7 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
         od[t] = dv;
     }
     if (cert.kind != NABO_CERT_NONE && lane == 0) {
-        const float tau = cert.tau[qi];
+        const float tau = tau_q;
         bool fail;
         if (tau == CUDART_INF_F) fail = n_valid < n_ref;          // nothing rejected <=> every reference is a candidate
         else if (n_finite < ksel) fail = true;
@@ -712,7 +742,8 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
 int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                        const int32_t* cand, int n_cand, const NaboCert& cert, int* fail_rows, int* fail_count,
-                       int32_t* out_idx, double* out_dist, const NaboRoute& route, cudaStream_t st) {
+                       int32_t* out_idx, double* out_dist, const NaboRoute& route, cudaStream_t st,
+                       const NaboCandBuf* from_buf) {
     NABO_ARG(n_cand >= 1 && n_cand <= 128, "rerank: n_cand=%d unsupported (1..128)", n_cand);
     NABO_ARG(k >= 1 && k + (drop_first ? 1 : 0) <= n_cand, "rerank: k=%d does not fit n_cand=%d", k, n_cand);
     if (n_query == 0) return 0;
@@ -720,10 +751,22 @@ int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n
     if (capp < 32) capp = 32;
     size_t smem = (size_t)4 * capp * (sizeof(double) + sizeof(int));
     dim3 grid((n_query + 3) / 4);
+    NaboCandBuf cb;
+    cb.buf = nullptr; cb.cnt = nullptr; cb.tau = nullptr; cb.kprime = 0;
+    if (from_buf) {
+        NABO_ARG(from_buf->kprime >= 1 && from_buf->kprime <= 64 && from_buf->kprime == n_cand,
+                 "rerank: buffer mode needs K' = n_cand <= 64");
+        cb = *from_buf;
+    }
 #define LAUNCH(M)                                                                                              \
-    rerank_kernel<M><<<grid, 128, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, drop_first,       \
-                                              idx_offset, cand, n_cand, capp, cert, fail_rows, fail_count,     \
-                                              out_idx, out_dist, route);
+    if (from_buf)                                                                                              \
+        rerank_kernel<M, true><<<grid, 128, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask,         \
+                                                        drop_first, idx_offset, cand, n_cand, capp, cert,      \
+                                                        fail_rows, fail_count, out_idx, out_dist, route, cb);  \
+    else                                                                                                       \
+        rerank_kernel<M, false><<<grid, 128, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask,        \
+                                                         drop_first, idx_offset, cand, n_cand, capp, cert,     \
+                                                         fail_rows, fail_count, out_idx, out_dist, route, cb);
     if (metric == NABO_EUCLIDEAN) { LAUNCH(NABO_EUCLIDEAN) }
     else if (metric == NABO_MOD_CANBERRA) { LAUNCH(NABO_MOD_CANBERRA) }
     else if (metric == NABO_COSINE) { LAUNCH(NABO_COSINE) }

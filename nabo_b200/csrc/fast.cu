@@ -106,10 +106,12 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
     float* tau = nullptr;
     double *qn2 = nullptr, *scal = nullptr;
     int kprime = 0, launches = 0;
+    NaboCandBuf raw;
+    raw.buf = nullptr;
     int n_split = nabo_tc_split(n_query, n_ref);              // > 1 only when there are fewer query items than SMs
     while (n_split > 1 && n_split * nabo_tc_kprime(k, drop_first) > 128) --n_split;     // the re-rank takes <= 128 candidates
     int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, mask, drop_first, &n_split, ar, &cand,
-                                &kprime, &tau, &qn2, &scal, &launches, tm, st);       // n_split out: K' lists per query
+                                &kprime, &tau, &qn2, &scal, &launches, tm, st, &raw);  // n_split out: K' lists per query
     if (rc) return rc;
     int* fail_rows = ar.take<int>(n_query);
     int* fail_count = ar.take<int>(1);
@@ -121,7 +123,8 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
     cert.tau = tau; cert.qn2 = qn2; cert.scal = scal; cert.c_acc = kCAcc;
     cert.abs_slack = 2.0 * sqrt((double)g) * 5.9604644775390625e-08;
     rc = nabo_rerank_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset, cand,
-                            kprime * n_split, cert, fail_rows, fail_count, out_idx, out_dist, route, st);
+                            kprime * n_split, cert, fail_rows, fail_count, out_idx, out_dist, route, st,
+                            raw.buf ? &raw : nullptr);
     if (rc) return rc;
     tm.end(1);
     // rows the certificate did not clear: exact brute force (grid sized for the worst case,

@@ -74,10 +74,20 @@ struct NaboCert {
                            // subnormal below |x| ~ 0.25, where the split error stops being relative)
 };
 
+// Candidates straight from the buffers the tensor-core sweep left behind (one 128-key buffer per query, query i at
+// slot i): the re-rank kernel makes the final K' selection itself (register bitonic sort) - no emit kernel, no
+// candidate-index round trip.  buf == NULL: candidates come from the `cand` lists.
+struct NaboCandBuf {
+    const unsigned long long* buf;   // [n_query][128] keys (score bits << 32 | reference row)
+    const int* cnt;                  // [n_query] live keys
+    const float* tau;                // [n_query] running threshold at the end of the sweep
+    int kprime;
+};
 int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                        const int32_t* cand, int n_cand, const NaboCert& cert, int* fail_rows, int* fail_count,
-                       int32_t* out_idx, double* out_dist, const NaboRoute& route, cudaStream_t st);
+                       int32_t* out_idx, double* out_dist, const NaboRoute& route, cudaStream_t st,
+                       const NaboCandBuf* from_buf = nullptr);
 
 struct NaboStageTimer;
 bool nabo_tc_supported(int g, int k, int drop_first);
@@ -88,7 +98,7 @@ int nabo_tc_split(int n_query, int n_ref);
 int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, const uint8_t* mask, int drop_first, int* n_split_io, NaboArena& ar, int32_t** cand_idx_out,
                        int* kprime_out, float** cert_tau_out, double** qn2_out, double** scal_out, int* launches,
-                       NaboStageTimer& tm, cudaStream_t st);
+                       NaboStageTimer& tm, cudaStream_t st, NaboCandBuf* raw_out = nullptr);
 
 bool nabo_cb_supported(int g, int k, int drop_first);
 int nabo_cb_kprime(int k, int drop_first);

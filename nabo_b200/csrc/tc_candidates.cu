@@ -892,7 +892,9 @@ size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_fi
 int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, const uint8_t* mask, int drop_first, int* n_split_io, NaboArena& ar, int32_t** cand_idx_out,
                        int* kprime_out, float** cert_tau_out, double** qn2_out, double** scal_out, int* launches,
-                       NaboStageTimer& tm, cudaStream_t st) {
+                       NaboStageTimer& tm, cudaStream_t st, NaboCandBuf* raw_out) {
+    // raw_out != NULL: when every query has ONE buffer in input order (MODE 0, no locality order, K' <= 64, 128-key
+    // buffers) the final selection is left to the re-rank kernel: raw_out is filled and no emit kernel runs.
     // *n_split_io in: reference pieces per item when there are few items (nabo_tc_split), or 0 = one piece and no
     // balancing of the last wave (the public candidate entry point: one K' list per query); out: K' lists per query
     int n_split = *n_split_io;
@@ -1016,6 +1018,14 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
 #undef NABO_TC_LAUNCH
     NABO_LAUNCH_CHECK("candidates_kernel");
     tm.end(0);             // the final selection below is timed with the re-rank stage
+    if (raw_out) raw_out->buf = nullptr;
+    if (raw_out && mode == 0 && !perm_q && kprime <= 64 && tc::CAP == 128) {
+        raw_out->buf = cbuf; raw_out->cnt = ccnt; raw_out->tau = ctau; raw_out->kprime = kprime;
+        *cand_idx_out = cand; *kprime_out = kprime; *cert_tau_out = tau; *qn2_out = qn2; *scal_out = scal;
+        *launches += 6;
+        *n_split_io = 1;
+        return 0;
+    }
     const unsigned egrid = (unsigned)((n_slots + 7) / 8);
     if (mode == 0 && perm_q) tc::emit_kernel<0, true><<<egrid, 256, 0, st>>>(p, n_slot_items, n_seg);
     else if (mode == 0) tc::emit_kernel<0, false><<<egrid, 256, 0, st>>>(p, n_slot_items, n_seg);
