@@ -9,51 +9,44 @@
 #define NABO_MERGE_MAX_SHARDS 16
 
 // ------------------------------------------------------------------ SNN counts + weights
-// One warp per query.  A = the query's k neighbours, sorted once in shared memory plus a 256-bit
-// signature; one neighbour's own kNN row per iteration, lanes over its entries (one coalesced row read):
-// an entry is binary-searched in A only if the signature admits it, and the row's intersection size
-// is the popcount of the warp's hit ballot (no atomics, no index arithmetic).
+// One warp per query.  A = the query's k neighbours go into a 256- (k <= 32) or 1024-slot open-addressing hash table in
+// shared memory; one neighbour's own kNN row per iteration, lanes over its entries (one coalesced row read): an
+// entry is a member of A iff a probe sequence of ~1.3 loads finds it, and the row's intersection size is the
+// popcount of the warp's hit ballot (no atomics in the counting, no index arithmetic).  The gathers of 16 rows are
+// issued back to back before any of them is consumed: the kernel is bound by L2 latency, not by arithmetic.
+__device__ __forceinline__ unsigned snn_hash(int v, unsigned mask) { return (((unsigned)v * 2654435761u) >> 16) & mask; }
+
 __global__ void __launch_bounds__(256)
-snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int kp2, const int32_t* __restrict__ ref_knn,
+snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int tsize, const int32_t* __restrict__ ref_knn,
            int n_ref, int k_ref, int k_use, const double* __restrict__ lut, uint8_t* __restrict__ counts,
            double* __restrict__ weights) {
     extern __shared__ int sm_snn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x * 8 + warp;
     if (t >= n_query) return;
-    int* a_sorted = sm_snn + warp * (2 * kp2 + k + 8);   // [kp2] sorted keys
-    int* a_row = a_sorted + kp2;                         // [kp2] the row in its own order
-    int* hits = a_row + kp2;                             // [k]   per-neighbour intersection size
-    unsigned* bloom = reinterpret_cast<unsigned*>(hits + k);   // 256-bit signature of the row's members
-    if (lane < 8) bloom[lane] = 0u;
-    for (int i = lane; i < kp2; i += 32) {
-        const int v = i < k ? tgt_knn[(long long)t * k + i] : -1;
-        a_sorted[i] = v >= 0 ? v : 0x7fffffff;           // missing neighbours never match
-        a_row[i] = v;
+    const int kp = (k + 31) & ~31;
+    int* table = sm_snn + warp * (tsize + 2 * kp);       // [tsize] hash table of A, -1 = empty
+    int* a_row = table + tsize;                          // [kp] the row in its own order
+    int* hits = a_row + kp;                              // [kp] per-neighbour intersection size
+    const unsigned mask = (unsigned)tsize - 1u;
+    for (int i = lane; i < tsize; i += 32) table[i] = -1;
+    for (int i = lane; i < kp; i += 32) {
+        a_row[i] = i < k ? tgt_knn[(long long)t * k + i] : -1;
+        hits[i] = 0;
     }
     __syncwarp();
     for (int i = lane; i < k; i += 32) {
         const int v = a_row[i];
         if (v >= 0) {
-            const unsigned h = ((unsigned)v * 2654435761u) >> 24;
-            atomicOr(&bloom[h >> 5], 1u << (h & 31));
+            unsigned s_ = snn_hash(v, mask);
+            for (;;) {
+                const int old = atomicCAS(&table[s_], -1, v);
+                if (old == -1 || old == v) break;
+                s_ = (s_ + 1) & mask;
+            }
         }
     }
-    // bitonic sort of the keys (ascending)
-    for (int size = 2; size <= kp2; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int e = lane; e < (kp2 >> 1); e += 32) {
-                const int lo = 2 * e - (e & (stride - 1)), hi = lo + stride;
-                const bool up = ((lo & size) == 0);
-                const int x = a_sorted[lo], y = a_sorted[hi];
-                if (up ? (y < x) : (x < y)) { a_sorted[lo] = y; a_sorted[hi] = x; }
-            }
-            __syncwarp();
-        }
-    // one neighbour row per iteration, lanes over its entries (one coalesced row read); an entry is looked up
-    // in the sorted row only if the signature says it may be a member (~1 in 9 of the non-members)
-    // (the gathers of 16 rows are issued back to back before any of them is consumed: the kernel is bound by
-    // L2 latency, not by arithmetic)
+    __syncwarp();
     for (int c0 = 0; c0 < k_use; c0 += 32) {
         const int col = c0 + lane;
         for (int r0 = 0; r0 < k; r0 += 16) {
@@ -69,18 +62,16 @@ snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int kp2, con
                 const int b = bv[u];
                 bool hit = false;
                 if (b >= 0) {
-                    const unsigned h = ((unsigned)b * 2654435761u) >> 24;
-                    if ((bloom[h >> 5] >> (h & 31)) & 1u) {
-                        int lo = 0, hi = kp2;            // first position with a_sorted[pos] >= b
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (a_sorted[mid] < b) lo = mid + 1; else hi = mid;
-                        }
-                        hit = lo < kp2 && a_sorted[lo] == b;
+                    unsigned s_ = snn_hash(b, mask);
+                    for (;;) {
+                        const int tv = table[s_];
+                        if (tv == b) { hit = true; break; }
+                        if (tv == -1) break;
+                        s_ = (s_ + 1) & mask;
                     }
                 }
                 const int cnt = __popc(__ballot_sync(0xffffffffu, hit));
-                if (lane == 0 && r0 + u < k) hits[r0 + u] = (c0 == 0 ? 0 : hits[r0 + u]) + cnt;
+                if (lane == 0 && r0 + u < k) hits[r0 + u] += cnt;
             }
         }
     }
@@ -101,10 +92,10 @@ extern "C" int nabo_snn_weights(const int32_t* tgt_knn, int n_query, int k, cons
     NABO_ARG(tgt_knn && ref_knn && (out_counts || out_weights), "snn: null pointer");
     NABO_ARG(!out_weights || lut, "snn: weights requested without a lut");
     int k_use = k < k_ref ? k : k_ref;   // ref_data[ref_c][:k], _mapping.py:193
-    int kp2 = nabo_next_pow2(k);
-    if (kp2 < 2) kp2 = 2;
-    snn_kernel<<<(n_query + 7) / 8, 256, 8 * (2 * kp2 + k + 8) * sizeof(int), (cudaStream_t)stream>>>(
-        tgt_knn, n_query, k, kp2, ref_knn, n_ref, k_ref, k_use, lut, out_counts, out_weights);
+    const int tsize = k <= 32 ? 256 : 1024;          // load factor <= 1/4: the warp walks the LONGEST probe sequence of its lanes
+    const int kp = (k + 31) & ~31;
+    snn_kernel<<<(n_query + 7) / 8, 256, 8 * (tsize + 2 * kp) * sizeof(int), (cudaStream_t)stream>>>(
+        tgt_knn, n_query, k, tsize, ref_knn, n_ref, k_ref, k_use, lut, out_counts, out_weights);
     NABO_LAUNCH_CHECK("snn_kernel");
     return 0;
 }
