@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--c5-ref", type=int, default=2_000_000)
     ap.add_argument("--c5-genes", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the config-5 block (one sample per GPU)")
     ap.add_argument("--no-projection", action="store_true", help="skip the projection (A1/A2) measurement")
     ap.add_argument("--no-ref-sharded", action="store_true", help="skip the reference-sharded (config 4) block")
     ap.add_argument("--ref-rows-per-gpu", type=int, default=1_250_000)
@@ -457,26 +458,18 @@ def score_determinism_check(dev, rank, world, ref, ref_knn, k, n_targets=65_536)
             "scores_sha256": hashlib.sha256(single.cpu().numpy().tobytes()).hexdigest()}
 
 
-def run_b200_config5(a):
-    """BASELINE config 5 (`--workload config5`): 8 target samples x --c5-cells cells of raw counts (--c5-genes HVG
-    columns) against a --c5-ref-cell reference in 50-PC space, cosine, k = 30, target-sharded: rank r maps samples
-    r, r + world, ...  One step = one sample through the whole path: counts -> scaling + projection (FP64 tensor-core
-    GEMM) -> cosine kNN (tcgen05 candidates + FP64 re-rank) -> SNN weights -> integer score accumulation.  The
-    per-reference scores of all samples are all-reduced once at the end (integers: same bits for any GPU count)."""
+def config5_block(a, dev, rank, world, steps, warmup, samples_per_gpu=None):
+    """BASELINE config 5: 8 target samples x --c5-cells cells of raw counts (--c5-genes HVG columns) against a
+    --c5-ref-cell reference in 50-PC space, cosine, k = 30, target-sharded: rank r maps samples r, r + world, ...
+    (samples_per_gpu = 1 inside the default line: ONE sample per GPU, so the block takes seconds at any GPU count).
+    One step = one sample through the whole path: counts -> scaling + projection (FP64 tensor-core GEMM) -> cosine
+    kNN (tcgen05 candidates + FP64 re-rank) -> SNN weights -> integer score accumulation.  The per-reference scores
+    of all samples are all-reduced once at the end (integers: same bits for any GPU count)."""
     import torch
     import torch.distributed as dist
-    from nabo_b200 import build, core, synth
+    from nabo_b200 import core, synth
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if a.gpus > 1 and world != a.gpus:
-        raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (a.gpus, a.gpus, world))
-    build.build()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    local = dev.index
     M, N, G, nc, k, n_samples = a.c5_ref, a.c5_cells, a.c5_genes, a.comps, a.k, 8
     t0 = time.perf_counter()
     ref = synth.pc_mixture_device(M, nc, seed=1, device=dev)
@@ -493,7 +486,7 @@ def run_b200_config5(a):
     x = probe * (1000.0 / torch.where(ptot > 0, ptot, torch.ones_like(ptot)))[:, None]
     mu, sigma = x.mean(0).to(torch.float64), x.std(0).to(torch.float64) + 1e-3
     gi = torch.arange(G, dtype=torch.int32, device=dev)
-    mine = list(range(rank, n_samples, world))
+    mine = list(range(rank, n_samples, world)) if samples_per_gpu is None else [rank % n_samples][:samples_per_gpu]
     samples = []
     for s_ in mine:
         c = synth.nb_counts_device(N, G, seed=100 + s_, device=dev)
@@ -518,21 +511,21 @@ def run_b200_config5(a):
         core.score_accumulate(idx, cnt, M, k, acc=acc)
         if marks:
             marks[4].record()
-            for j, n_ in enumerate(("projection", "knn", "snn", "scores")):
-                stage[n_].append((marks[j], marks[j + 1]))
+            for j_, n_ in enumerate(("projection", "knn", "snn", "scores")):
+                stage[n_].append((marks[j_], marks[j_ + 1]))
         return idx, dst, w
 
-    for i in range(a.warmup):
+    for i in range(warmup):
         step(i)
     acc.zero_()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     sampler = ClockSampler(local)
     sampler.start()
-    for i in range(a.steps):
+    for i in range(steps):
         ev[i][0].record()
         step(i)
         ev[i][1].record()
@@ -544,33 +537,59 @@ def run_b200_config5(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-    scores = core.scores_finalize(acc, world * a.steps * N)
-    for i in range(min(2, a.steps)):
+    scores = core.scores_finalize(acc, world * steps * N)
+    for i in range(min(2, steps)):
         step(i, timed_stages=True)
     torch.cuda.synchronize()
-    ms_step = float(t.item()) / a.steps
+    ms_step = float(t.item()) / steps
+    mean_ms = {n_: sum(_ev_ms(p_)) / max(1, len(p_)) for n_, p_ in stage.items()}
+    block = {
+        "workload": "config5: %d cells x %d HVG counts per sample -> %d PCs -> cosine kNN (k=%d) against %d reference cells -> "
+                    "SNN weights -> mapping scores; target-sharded, %d sample(s) per GPU" % (N, G, nc, k, M, len(mine)),
+        "value": world * N / (ms_step / 1e3), "unit": "cells/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
+        "stage_ms": mean_ms,
+        "projection_tflops_fp64": 2.0 * G * nc * N / (max(1e-9, mean_ms["projection"]) * 1e-3) / 1e12,
+        "knn_pairs_per_s": float(N) * M / (max(1e-9, mean_ms["knn"]) * 1e-3),
+        "reference_cells_with_a_score": int((scores > 0).sum()), "setup_s": setup_s, "clocks": clocks,
+    }
+    del samples, ref, ref_knn, acc, pca
+    torch.cuda.empty_cache()
+    return block
+
+
+def run_b200_config5(a):
+    """`--workload config5`: the config-5 block with all 8 samples dealt over the GPUs, as the whole line."""
+    import torch
+    import torch.distributed as dist
+    from nabo_b200 import build
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus > 1 and world != a.gpus:
+        raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (a.gpus, a.gpus, world))
+    build.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b = config5_block(a, dev, rank, world, a.steps, a.warmup)
     peaks = load_peaks()
+    ach = 2.0 * a.comps * b["knn_pairs_per_s"] / 1e12
     line = {
-        "metric": "target_cells_mapped_per_s", "value": world * N / (ms_step / 1e3), "unit": "cells/s", "n_gpus": world,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "metric": "target_cells_mapped_per_s", "value": b["value"], "unit": "cells/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": b["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 (projection: f64 DMMA; candidates: f16x2-split tcgen05, f32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": "config5: %d samples x %d cells x %d HVG counts -> %d PCs -> cosine kNN (k=%d) against %d "
-                               "reference cells -> SNN weights -> mapping scores; target-sharded, %d sample(s) per GPU"
-                               % (n_samples, N, G, nc, k, M, len(mine)),
-                   "engine": a.engine, "l2": "inputs (4 GB of counts per sample) exceed L2", "inputs_resident": True},
-        "clocks": clocks,
-        "stage_ms": {n_: sum(_ev_ms(p_)) / max(1, len(p_)) for n_, p_ in stage.items()},
-        "projection_tflops_fp64": 2.0 * G * nc * N / (max(1e-9, sum(_ev_ms(stage["projection"])) / max(1, len(stage["projection"]))) * 1e-3) / 1e12,
-        "knn_pairs_per_s": float(N) * M / (max(1e-9, sum(_ev_ms(stage["knn"])) / max(1, len(stage["knn"]))) * 1e-3),
-        "scores_sha256_note": "integer weight sums all-reduced once; nonzero reference cells: %d" % int((scores > 0).sum()),
-        "e2e": None, "gpu_launches": None, "cpu_baseline": None, "setup_s": setup_s,
-        "roofline": {"bound": "tmem-read / tensor", "kernel": "tc::candidates_kernel", "unit": "TFLOP/s",
-                     "achieved": 2.0 * nc * N * M / (max(1e-9, sum(_ev_ms(stage["knn"])) / max(1, len(stage["knn"]))) * 1e-3) / 1e12,
-                     "peak": peaks["bf16_tflops_sustained"], "traffic": None,
+        "config": {"workload": b["workload"], "engine": a.engine, "l2": "inputs (4 GB of counts per sample) exceed L2",
+                   "inputs_resident": True},
+        "clocks": b["clocks"], "stage_ms": b["stage_ms"], "projection_tflops_fp64": b["projection_tflops_fp64"],
+        "knn_pairs_per_s": b["knn_pairs_per_s"], "e2e": None, "gpu_launches": None, "cpu_baseline": None,
+        "setup_s": b["setup_s"],
+        "roofline": {"bound": "tmem-read / tensor", "kernel": "tc::candidates_kernel", "unit": "TFLOP/s", "achieved": ach,
+                     "peak": peaks["bf16_tflops_sustained"], "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
                      "note": "whole kNN call (candidates + re-rank), 2*g flop per pair"},
     }
-    line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -773,6 +792,9 @@ def run_b200(a):
         line["ref_sharded"] = ref_sharded_block(a, dev, rank, world, a.ref_rows_per_gpu, a.ref_batch, 5,
                                                 max(5, a.steps // 2), 2)
         line["score_determinism"] = score_determinism_check(dev, rank, world, ref, ref_knn, k)
+        if not a.no_config5:
+            # BASELINE config 5 under the same clock: one sample (500 k cells of counts) per GPU against a 2 M reference
+            line["config5"] = config5_block(a, dev, rank, world, 2, 1, samples_per_gpu=1)
     if rank == 0 and not a.no_projection:
         line["projection"] = projection_block(dev)
     if world > 1:

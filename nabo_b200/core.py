@@ -649,6 +649,7 @@ class _HostPipeline:
 
 
 _PIPE: Dict[tuple, _HostPipeline] = {}
+_WAVE = 148 * 384         # queries one wave of the persistent candidate kernel maps (one 384-query work item per SM)
 
 
 def map_cells_host(target_host: torch.Tensor, ref, ref_knn, k: int, metric: Optional[str] = None,
@@ -673,6 +674,12 @@ def map_cells_host(target_host: torch.Tensor, ref, ref_knn, k: int, metric: Opti
     comp = torch.cuda.current_stream()
     chunks = max(1, min(int(chunks), n // int(min_piece) if n >= 2 * int(min_piece) else 1))
     bounds = [n * i // chunks for i in range(chunks + 1)]
+    if chunks == 2 and n > _WAVE:
+        # the first piece's upload and the last piece's download are the exposed copies: make the first piece the
+        # smaller one, and the last one whole waves of the persistent candidate kernel (148 SMs x 384 queries)
+        last = (n // 2 + _WAVE - 1) // _WAVE * _WAVE
+        if 0 < n - last < n:
+            bounds = [0, n - last, n]
     pipe.s_in.wait_stream(comp)
     pipe.s_out.wait_stream(comp)
     pipe.acc.zero_()
@@ -686,15 +693,19 @@ def map_cells_host(target_host: torch.Tensor, ref, ref_knn, k: int, metric: Opti
     for (lo, hi), ev in zip(zip(bounds, bounds[1:]), ready):
         comp.wait_event(ev)
         knn(pipe.dev_in[lo:hi], rd, k, met, dist_factor, ref_mask, False, 0, mode, out=(pipe.idx[lo:hi], pipe.dist[lo:hi]))
+        found = torch.cuda.Event()
+        found.record(comp)
+        with torch.cuda.stream(pipe.s_out):                 # neighbours go home while the weights are still being made
+            pipe.s_out.wait_event(found)
+            pipe.host["idx"][lo:hi].copy_(pipe.idx[lo:hi], non_blocking=True)
+            pipe.host["dist"][lo:hi].copy_(pipe.dist[lo:hi], non_blocking=True)
         snn_weights(pipe.idx[lo:hi], rk, k, out=(pipe.cnt[lo:hi], pipe.w[lo:hi]))
-        score_accumulate(pipe.idx[lo:hi], pipe.cnt[lo:hi], m, k, acc=pipe.acc)     # integer sums: piece order is immaterial
         done = torch.cuda.Event()
         done.record(comp)
         with torch.cuda.stream(pipe.s_out):
             pipe.s_out.wait_event(done)
-            pipe.host["idx"][lo:hi].copy_(pipe.idx[lo:hi], non_blocking=True)
-            pipe.host["dist"][lo:hi].copy_(pipe.dist[lo:hi], non_blocking=True)
             pipe.host["weights"][lo:hi].copy_(pipe.w[lo:hi], non_blocking=True)
+        score_accumulate(pipe.idx[lo:hi], pipe.cnt[lo:hi], m, k, acc=pipe.acc)     # integer sums: piece order is immaterial
     sc = scores_finalize(pipe.acc, n)
     pipe.host["scores"].copy_(sc, non_blocking=True)
     comp.synchronize()

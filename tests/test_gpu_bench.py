@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_bench_line_has_the_contract_keys():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3",
-                          "--n-ref", "30000", "--n-query", "30000", "--cpu-seconds", "1"],
+                          "--n-ref", "30000", "--n-query", "30000", "--cpu-seconds", "1", "--no-config5",
+                          "--ref-rows-per-gpu", "300000", "--ref-batch", "60000"],
                          capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
@@ -31,3 +32,10 @@ def test_bench_line_has_the_contract_keys():
     assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] > 0 and "sample" in cpu
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(line["clocks"])
     assert line["mod_canberra"]["value"] > 0 and line["rows_exact_fallback_per_step"] == 0
+    assert line["mod_canberra"]["roofline"]["bound"] == "alu" and 0 < line["mod_canberra"]["roofline"]["frac"] < 1
+    assert 0 < roof["tmem_readout"]["frac"] < 1.05
+    rs = line["ref_sharded"]
+    assert rs["value"] > 0 and rs["parity"]["idx_equal"] and rs["parity"]["dist_bit_equal"] and rs["parity"]["weights_bit_equal"]
+    assert set(("knn_candidates", "knn_rerank", "exchange", "merge", "snn", "scores")) <= set(rs["stage_ms"])
+    assert line["score_determinism"]["bit_identical_single_vs_target_sharded_vs_reference_sharded"] is True
+    assert line["projection"]["config1"]["mma"]["ms"] > 0 and line["projection"]["config5_slice"]["mma"]["fp64_tflops"] > 1
