@@ -85,6 +85,43 @@ __device__ __forceinline__ void warp_bitonic_sort(double* d, int* idx, int n, in
     }
 }
 
+// The same order for NU * 32 pairs held in registers: position u * 32 + lane is slot u of lane `lane`.  Strides below
+// 32 exchange through shuffles, strides of 32 and more are register swaps inside the lane; no shared memory.
+template <int NU>
+__device__ __forceinline__ void warp_bitonic_sort_regs(double (&d)[NU], int (&ix)[NU], int lane) {
+#pragma unroll
+    for (int size = 2; size <= NU * 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int su = stride >> 5;
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    if (u & su) continue;
+                    const bool up = (((u << 5) | lane) & size) == 0;
+                    const int v = u | su;
+                    const bool sw = up ? nabo_less(d[v], ix[v], d[u], ix[u]) : nabo_less(d[u], ix[u], d[v], ix[v]);
+                    const double dl = d[u], dh = d[v];
+                    const int il = ix[u], ih = ix[v];
+                    d[u] = sw ? dh : dl; d[v] = sw ? dl : dh;
+                    ix[u] = sw ? ih : il; ix[v] = sw ? il : ih;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const bool up = (((u << 5) | lane) & size) == 0;
+                    const bool want_min = ((lane & stride) == 0) == up;
+                    const double pd = __shfl_xor_sync(0xffffffffu, d[u], stride);
+                    const int pi = __shfl_xor_sync(0xffffffffu, ix[u], stride);
+                    const bool take = want_min ? nabo_less(pd, pi, d[u], ix[u]) : nabo_less(d[u], ix[u], pd, pi);
+                    d[u] = take ? pd : d[u];
+                    ix[u] = take ? pi : ix[u];
+                }
+            }
+        }
+    }
+}
+
 // Same for packed 64-bit keys (sortable-float << 32 | index).
 __device__ __forceinline__ void warp_bitonic_sort_u64(unsigned long long* a, int n, int lane) {
     for (int size = 2; size <= n; size <<= 1) {

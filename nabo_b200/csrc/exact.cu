@@ -640,6 +640,41 @@ __device__ __forceinline__ double cert_lower_bound(const NaboCert& c, int qi, fl
     return 0.5 * e * e * (1.0 - 1e-9);
 }
 
+// acc[u] = sum over the dimensions of the pair terms of (x, row jj[u] of r), u < NU, all slots in one sweep over the
+// dimensions.  Slots without a candidate (jj < 0) read row 0 and are ignored by the caller.  vec2: r is 16-byte
+// aligned with an even leading dimension, rows are read as double2.
+template <int METRIC, int NU>
+__device__ __forceinline__ void pair_rows(const double* __restrict__ x, const double* __restrict__ r, int ldr,
+                                          const int* jj, int g, double f, bool vec2, double* acc) {
+    const double* y[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) y[u] = r + (long long)(jj[u] >= 0 ? jj[u] : 0) * ldr;
+    double a[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) a[u] = 0.0;
+    int kk = 0;
+    if (vec2) {
+#pragma unroll 4
+        for (; kk + 2 <= g; kk += 2) {
+            const double x0 = x[kk], x1 = x[kk + 1];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const double2 v = __ldg(reinterpret_cast<const double2*>(y[u] + kk));
+                a[u] = Pair<METRIC>::step(a[u], x0, v.x, f);
+                a[u] = Pair<METRIC>::step(a[u], x1, v.y, f);
+            }
+        }
+    }
+#pragma unroll 4
+    for (; kk < g; ++kk) {
+        const double xv = x[kk];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) a[u] = Pair<METRIC>::step(a[u], xv, __ldg(y[u] + kk), f);
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) acc[u] = a[u];
+}
+
 template <int METRIC, bool FROM_BUF>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ r, int ldr, int n_query,
@@ -647,7 +682,7 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
               int idx_offset, const int32_t* __restrict__ cand, int n_cand, int capp, const NaboCert cert,
               int* __restrict__ fail_rows, int* __restrict__ fail_count,
               int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const NaboRoute route,
-              const NaboCandBuf cb) {
+              const NaboCandBuf cb, int xs_dims, bool vec2) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = blockIdx.x * 4 + warp;
@@ -683,37 +718,75 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
     } else if (cert.kind != NABO_CERT_NONE) {
         tau_q = cert.tau[qi];
     }
-    int n_valid = 0, n_finite = 0;
+    // The query in shared memory (broadcast reads), then every lane walks the rows of its candidates - slot u of a
+    // lane is candidate u * 32 + lane - for all its slots in ONE loop over the dimensions: the loads of different
+    // slots are independent, the additions of one slot stay in dimension order (bit-identical to the exact engine).
+    double* xw = xs_dims ? smem + (size_t)4 * capp + (size_t)(4 * capp + 1) / 2 + (size_t)warp * xs_dims : nullptr;
+    if (xw) {
+        for (int kk = lane; kk < g; kk += 32) xw[kk] = x[kk];
+        __syncwarp();
+    }
+    const double* xq = xw ? xw : x;
+    int jj[4];
+    int n_slots = 0;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int c = u * 32 + lane;
-        if (u * 32 >= capp) break;
-        int j;
-        if (FROM_BUF) j = (u < 2 && c < nc) ? (int)kpl[u] : -1;
-        else j = c < n_cand ? cand[(long long)qi * n_cand + c] : -1;
+        int j = -1;
+        if (u * 32 < capp) {
+            if (FROM_BUF) j = (u < 2 && c < nc) ? (int)kpl[u] : -1;
+            else j = c < n_cand ? cand[(long long)qi * n_cand + c] : -1;
+        }
+        if (!(j >= 0 && j < n_ref)) j = -1;
+        jj[u] = j;
+        if (__any_sync(0xffffffffu, j >= 0)) n_slots = u + 1;
+    }
+    double accs[4] = {0.0, 0.0, 0.0, 0.0};
+    if (n_slots == 1) pair_rows<METRIC, 1>(xq, r, ldr, jj, g, f, vec2, accs);
+    else if (n_slots == 2) pair_rows<METRIC, 2>(xq, r, ldr, jj, g, f, vec2, accs);
+    else if (n_slots > 2) pair_rows<METRIC, 4>(xq, r, ldr, jj, g, f, vec2, accs);
+    int n_valid = 0, n_finite = 0;
+    int ids[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = jj[u];
         double key = CUDART_INF;
         int id = 0x7fffffff;
-        if (j >= 0 && j < n_ref) {
-            const double* y = r + (long long)j * ldr;
-            double acc = 0.0;
-            for (int kk = 0; kk < g; ++kk) acc = Pair<METRIC>::step(acc, x[kk], y[kk], f);
+        if (j >= 0) {
             double nr = 0.0;
-            if (METRIC == NABO_COSINE) nr = seq_sqnorm(y, g);
-            double dv = Pair<METRIC>::finish(acc, nq, nr);
+            if (METRIC == NABO_COSINE) nr = seq_sqnorm(r + (long long)j * ldr, g);
+            double dv = Pair<METRIC>::finish(accs[u], nq, nr);
             if (dv != dv || (mask && mask[j])) dv = CUDART_INF;
             key = dv;
             id = j;
             ++n_valid;
             n_finite += (dv < CUDART_INF);
         }
-        d[c] = key; ix[c] = id;
+        accs[u] = key; ids[u] = id;
+    }
+    // ascending (distance, index) order in registers, then into the warp's shared-memory row for the indexed reads below
+    if (capp <= 32) {
+        double d1[1] = {accs[0]};
+        int i1[1] = {ids[0]};
+        warp_bitonic_sort_regs<1>(d1, i1, lane);
+        d[lane] = d1[0]; ix[lane] = i1[0];
+    } else if (capp <= 64) {
+        double d2[2] = {accs[0], accs[1]};
+        int i2[2] = {ids[0], ids[1]};
+        warp_bitonic_sort_regs<2>(d2, i2, lane);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { d[u * 32 + lane] = d2[u]; ix[u * 32 + lane] = i2[u]; }
+    } else {
+        warp_bitonic_sort_regs<4>(accs, ids, lane);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { d[u * 32 + lane] = accs[u]; ix[u * 32 + lane] = ids[u]; }
     }
     __syncwarp();
     for (int o = 16; o > 0; o >>= 1) {
         n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
         n_finite += __shfl_xor_sync(0xffffffffu, n_finite, o);
     }
-    warp_bitonic_sort(d, ix, capp, lane);
+    __syncwarp();
     const int skip = drop_first ? 1 : 0;
     const int ksel = k + skip;
     for (int t = lane; t < k; t += 32) {
@@ -750,6 +823,9 @@ int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n
     int capp = nabo_next_pow2(n_cand);
     if (capp < 32) capp = 32;
     size_t smem = (size_t)4 * capp * (sizeof(double) + sizeof(int));
+    const int xs_dims = g <= 1024 ? g : 0;                 // the query rides in shared memory when it is short enough
+    smem += (size_t)4 * xs_dims * sizeof(double);
+    const bool vec2 = ((uintptr_t)r & 15) == 0 && (ldr & 1) == 0;
     dim3 grid((n_query + 3) / 4);
     NaboCandBuf cb;
     cb.buf = nullptr; cb.cnt = nullptr; cb.tau = nullptr; cb.kprime = 0;
@@ -762,11 +838,11 @@ int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n
     if (from_buf)                                                                                              \
         rerank_kernel<M, true><<<grid, 128, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask,         \
                                                         drop_first, idx_offset, cand, n_cand, capp, cert,      \
-                                                        fail_rows, fail_count, out_idx, out_dist, route, cb);  \
+                                                        fail_rows, fail_count, out_idx, out_dist, route, cb, xs_dims, vec2);  \
     else                                                                                                       \
         rerank_kernel<M, false><<<grid, 128, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask,        \
                                                          drop_first, idx_offset, cand, n_cand, capp, cert,     \
-                                                         fail_rows, fail_count, out_idx, out_dist, route, cb);
+                                                         fail_rows, fail_count, out_idx, out_dist, route, cb, xs_dims, vec2);
     if (metric == NABO_EUCLIDEAN) { LAUNCH(NABO_EUCLIDEAN) }
     else if (metric == NABO_MOD_CANBERRA) { LAUNCH(NABO_MOD_CANBERRA) }
     else if (metric == NABO_COSINE) { LAUNCH(NABO_COSINE) }
