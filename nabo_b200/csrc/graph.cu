@@ -35,18 +35,26 @@ snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int tsize, c
         hits[i] = 0;
     }
     __syncwarp();
+    // insert; the warp remembers the LONGEST displacement of any key, so that a lookup is a fixed number of
+    // independent probes (no data-dependent loop, no divergence): 1 + disp slots, disp is 0 or 1 at this load factor
+    int disp = 0;
     for (int i = lane; i < k; i += 32) {
         const int v = a_row[i];
         if (v >= 0) {
             unsigned s_ = snn_hash(v, mask);
+            int dd = 0;
             for (;;) {
                 const int old = atomicCAS(&table[s_], -1, v);
                 if (old == -1 || old == v) break;
                 s_ = (s_ + 1) & mask;
+                ++dd;
             }
+            disp = max(disp, dd);
         }
     }
+    disp = __reduce_max_sync(0xffffffffu, disp);
     __syncwarp();
+    // the ballot count of a row is warp-uniform: row r0 + u of a block of 16 accumulates in lane (r0 & 31) + u
     for (int c0 = 0; c0 < k_use; c0 += 32) {
         const int col = c0 + lane;
         for (int r0 = 0; r0 < k; r0 += 16) {
@@ -57,22 +65,24 @@ snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int tsize, c
                 const int j = row < k ? a_row[row] : -1;
                 bv[u] = (j >= 0 && j < n_ref && col < k_use) ? __ldg(ref_knn + (long long)j * k_ref + col) : -1;
             }
+            const int base = r0 & 31;
+            int blk = 0;
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
                 const int b = bv[u];
-                bool hit = false;
-                if (b >= 0) {
-                    unsigned s_ = snn_hash(b, mask);
-                    for (;;) {
-                        const int tv = table[s_];
-                        if (tv == b) { hit = true; break; }
-                        if (tv == -1) break;
-                        s_ = (s_ + 1) & mask;
-                    }
+                const unsigned s_ = snn_hash(b, mask);
+                bool hit;
+                if (disp <= 1) {
+                    hit = (table[s_] == b) | (table[(s_ + 1) & mask] == b);
+                } else {
+                    hit = false;
+                    for (int dd = 0; dd <= disp; ++dd) hit |= table[(s_ + dd) & mask] == b;
                 }
-                const int cnt = __popc(__ballot_sync(0xffffffffu, hit));
-                if (lane == 0 && r0 + u < k) hits[r0 + u] += cnt;
+                const int cnt = __popc(__ballot_sync(0xffffffffu, hit && b >= 0));
+                if (lane == base + u) blk += cnt;
             }
+            const int mine = r0 + lane - base;
+            if (lane >= base && lane < base + 16 && mine < k) hits[mine] += blk;
         }
     }
     __syncwarp();

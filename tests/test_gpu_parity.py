@@ -183,7 +183,8 @@ def test_golden_c1(core, golden, mode):
 
 
 # ------------------------------------------------------------------ SNN / scores / classify / merge
-@pytest.mark.parametrize("n,m,k", [(1, 40, 5), (333, 500, 30), (1000, 200, 11)])
+# k = 130 / 200: the 1 024-slot table at 13 % / 20 % load, keys displaced by two and more slots (the generic probe path)
+@pytest.mark.parametrize("n,m,k", [(1, 40, 5), (333, 500, 30), (1000, 200, 11), (64, 300, 130), (200, 400, 200)])
 def test_snn_and_scores_oracle(core, n, m, k):
     rng = np.random.default_rng(n + m + k)
     ref_knn = np.array([rng.choice(m, size=k, replace=False) for _ in range(m)], dtype=np.int32)
