@@ -31,18 +31,48 @@
 #include "ptx.cuh"
 #include "select.cuh"
 
+#ifndef NABO_CBS_NBINS
+#define NABO_CBS_NBINS 32
+#endif
+#ifndef NABO_CBS_RT
+#define NABO_CBS_RT 128
+#endif
+#ifndef NABO_CBS_DUAL
+#define NABO_CBS_DUAL 1              // two work-list entries per lane and evaluation pass when more than 32 are left
+#endif
 #ifndef NABO_CBS_SLEEP_NS
 #define NABO_CBS_SLEEP_NS 400        // suspend-time hint of the tile waits (0 = plain polling)
 #endif
 
 namespace cbs {
 
+#ifdef NABO_CBS_PROF       // development cycle accounting of a busy warp's sweep (tools/probe_cb_prof.py):
+                           // [0] tile waits [1] count bound [2] work list [3] FP32 evaluation [4] compaction
+                           // [5] stage release [6] round set-up + final selection [7] busy warp-tiles [8] evaluation passes
+                           // [9] compactions [10] survivors
+__device__ unsigned long long g_cbs_prof[12];
+#define CBS_PROF_DECL long long prof_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t_ = clock64();
+#define CBS_PROF(i) { const long long t1_ = clock64(); prof_[i] += t1_ - prof_t_; prof_t_ = t1_; }
+#define CBS_PROF_COUNT(i, n) prof_[i] += (n);
+#define CBS_PROF_FLUSH if (lane == 0) { for (int i_ = 0; i_ < 12; ++i_) atomicAdd(&g_cbs_prof[i_], (unsigned long long)prof_[i_]); }
+#else
+#define CBS_PROF_DECL
+#define CBS_PROF(i)
+#define CBS_PROF_COUNT(i, n)
+#define CBS_PROF_FLUSH
+#endif
+
 using namespace sel;   // make_key, compact_select, compact_sort_inline
 
-constexpr int NBINS = 32;                 // value bins per dimension
-constexpr int NPL = NBINS + 1;            // cumulative planes per (dimension, word)
-constexpr int RT = 128;                   // references per tile
+constexpr int NBINS = NABO_CBS_NBINS;     // value bins per dimension
+constexpr int RT = NABO_CBS_RT;           // references per tile (64 or 128)
 constexpr int WPT = RT / 32;              // words per tile
+constexpr int T64 = RT / 64;              // 64-reference blocks of the FP32 copy per tile
+// cumulative planes per (dimension, word): NBINS + 1, padded so that a (dimension) row of WPT words is a multiple
+// of 16 bytes (bulk copies) - the pad planes are never read
+constexpr int NPL = (WPT % 4 == 0) ? NBINS + 1 : ((NBINS + 1 + 1) & ~1);
+static_assert(RT == 64 || RT == 128, "tile = 64 or 128 references");
+static_assert(NBINS >= 2 && NBINS <= 128 && (WPT * NPL) % 4 == 0, "plane rows must be multiples of 16 bytes");
 constexpr int NW = 12;                    // warps per CTA
 constexpr int QB = NW * 32;               // queries a CTA handles per round (at most)
 constexpr int NTHREADS = NW * 32;
@@ -140,12 +170,12 @@ planes_kernel(const float* __restrict__ rt, const float* __restrict__ edges, con
     uint32_t* out = planes + (((size_t)tile * g + k) * WPT + w) * NPL;
 #pragma unroll
     for (int p = 0; p < NPL; ++p) {
-        const uint32_t bits = __ballot_sync(0xffffffffu, live && b < p);
+        const uint32_t bits = __ballot_sync(0xffffffffu, live && b < p && p <= NBINS);
         if (lane == (p & 31)) out[p] = bits;
     }
 }
 
-// Per (query, dimension) plane byte offsets: low byte = 4 * lo, high byte = 4 * (hi + 1), 0 / 0 for an empty
+// Per (query, dimension) plane indices: low byte = lo, high byte = hi + 1, 0 / 0 for an empty
 // interval (x = 0 or NaN: nothing is unsaturated).  Two dimensions per 32-bit word, lanes interleaved:
 // ctrl[(group32 * nj + j) * 32 + lane].  The interval is widened by 1e-6 relative (FP64 rounding of the
 // reference's own test) and its end points are rounded outward to FP32 - the precision the planes were
@@ -177,7 +207,7 @@ ctrl_kernel(const double* __restrict__ q, int ld, int n_query, int g, int nj, do
                 }
                 if (!(hi_v == hi_v)) hi = NBINS - 1;      // x + t overflowed to NaN / inf: keep everything
                 if (!(lo_v == lo_v)) lo = 0;
-                c = (uint32_t)(lo * 4) | ((uint32_t)((hi + 1) * 4) << 8);
+                c = (uint32_t)lo | ((uint32_t)(hi + 1) << 8);
             }
         }
         word |= c << (16 * h);
@@ -216,6 +246,12 @@ struct Barriers {
     uint64_t full[MAX_STAGES];
     int done[MAX_STAGES];
 };
+
+__device__ __forceinline__ float rcp_approx(float x) {       // MUFU.RCP, 1 ulp: inside the nabo_cb_eps margin
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 #define NABO_CSA(h, l, a, b, c)                           \
     {                                                     \
@@ -268,7 +304,7 @@ sliced_kernel(const Params p) {
     const uint32_t plane_bytes = (uint32_t)((size_t)g * WPT * NPL * 4);
     auto issue_tile = [&](uint32_t tn, uint32_t s) {          // one thread
         const int j = tile0 + (int)(tn % (uint32_t)n_tiles);
-        const int n64 = min(2, p.n_tiles64 - 2 * j);
+        const int n64 = min(T64, p.n_tiles64 - T64 * j);
         const uint32_t ys_bytes = (uint32_t)n64 * g * 64 * 4;
         ptx::mbar_arrive_expect_tx(&bars->full[s], plane_bytes + ys_bytes);
         char* dst = reinterpret_cast<char*>(smem + p.stage_off + (size_t)s * p.stage_bytes);
@@ -276,7 +312,7 @@ sliced_kernel(const Params p) {
         for (uint32_t o = 0; o < plane_bytes; o += 16384)
             ptx::bulk_g2s(dst + o, src + o, min(16384u, plane_bytes - o), &bars->full[s]);
         dst += plane_bytes;
-        src = reinterpret_cast<const char*>(p.rt) + (size_t)j * 2 * g * 64 * 4;
+        src = reinterpret_cast<const char*>(p.rt) + (size_t)j * T64 * g * 64 * 4;
         for (uint32_t o = 0; o < ys_bytes; o += 16384)
             ptx::bulk_g2s(dst + o, src + o, min(16384u, ys_bytes - o), &bars->full[s]);
     };
@@ -310,43 +346,93 @@ sliced_kernel(const Params p) {
     const float fm = p.fm;
     const int kprime = p.kprime;
 
-    // dense FP32 evaluation of the first n work-list entries of the current tile
+    // dense FP32 evaluation of the first n work-list entries of the current tile.  A lane takes TWO entries per pass
+    // (NABO_CBS_DUAL) when more than 32 are left: the two dependency chains (load, rcp, select, add) interleave, and a
+    // warp's sweep is latency-bound.  A pass then adds at most 64 keys to one query, so the buffers are kept at or
+    // below CAP - 64 (dual passes are used only when kprime + trig_extra allows that).
+    CBS_PROF_DECL
+    const int trig = min(CAP - 32, kprime + p.trig_extra);
+    const bool dual_ok = NABO_CBS_DUAL && trig <= CAP - 64;
+    auto compact_due = [&]() {
+        // compacting earlier than the buffer limit (kprime + trig_extra keys) keeps tau closer to the true running
+        // K'-th best score: a stale threshold lets proportionally more pairs through to the dense evaluation
+        unsigned need = __ballot_sync(0xffffffffu, s_cnt[lane] > trig);
+        if (need) CBS_PROF(3)
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            int nc;
+            float nt;
+            compact_select<4>(gbuf + (size_t)src * CAP, s_cnt[src], lane, kprime, trig - 4 > kprime ? trig - 4 : kprime, hist, nc, nt);
+            if (lane == src) { s_cnt[lane] = nc; s_tau[lane] = nt; }
+            __syncwarp();
+            CBS_PROF_COUNT(9, 1)
+            CBS_PROF(4)
+        }
+    };
     auto evaluate = [&](int n, const float* ys, int ref0) {
-        for (int base = 0; base < n; base += 32) {
-            const int i = base + lane;
-            const bool active = i < n;
-            const int e = active ? work[i] : 0;
-            const int ql = e >> 8, rl = e & 127;
-            const float* xb = xs + ql;
-            const float* yb = ys + (rl >> 6) * (g * 64) + (rl & 63);
-            float acc = 0.f;
+        int base = 0;
+        CBS_PROF_COUNT(10, n)
+        while (base < n) {
+            CBS_PROF_COUNT(8, 1)
+            if (dual_ok && n - base > 32) {
+                const int i0 = base + lane, i1 = base + 32 + lane;
+                const bool act1 = i1 < n;
+                const int e0 = work[i0], e1 = act1 ? work[i1] : 0;
+                const int ql0 = e0 >> 8, rl0 = e0 & 127, ql1 = e1 >> 8, rl1 = e1 & 127;
+                const float* xb0 = xs + ql0;
+                const float* yb0 = ys + (rl0 >> 6) * (g * 64) + (rl0 & 63);
+                const float* xb1 = xs + ql1;
+                const float* yb1 = ys + (rl1 >> 6) * (g * 64) + (rl1 & 63);
+                float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 5
-            for (int k = 0; k < g; ++k) {
-                const float x = xb[k * 32], y = yb[k * 64];
-                const float num = fabsf(x - y), xa = fabsf(x);
-                const float term = __fdividef(num, xa + (fabsf(y) + 0.01f));
-                acc += (num < fm * xa) ? term : 1.0f;
-            }
-            if (active && acc < s_tau[ql]) {
-                const int pos = atomicAdd(&s_cnt[ql], 1);
-                NABO_DEV_ASSERT(pos >= 0 && pos < CAP && ql >= 0 && ql < 32);
-                gbuf[(size_t)ql * CAP + pos] = make_key(acc, (uint32_t)(ref0 + rl));
+                for (int k = 0; k < g; ++k) {
+                    const float x0 = xb0[k * 32], y0 = yb0[k * 64];
+                    const float x1 = xb1[k * 32], y1 = yb1[k * 64];
+                    const float num0 = fabsf(x0 - y0), xa0 = fabsf(x0);
+                    const float num1 = fabsf(x1 - y1), xa1 = fabsf(x1);
+                    const float term0 = fmaf(num0, rcp_approx(xa0 + (fabsf(y0) + 0.01f)), -1.0f);
+                    const float term1 = fmaf(num1, rcp_approx(xa1 + (fabsf(y1) + 0.01f)), -1.0f);
+                    if (num0 < fm * xa0) acc0 += term0;           // distance = g + sum over the unsaturated of (term - 1)
+                    if (num1 < fm * xa1) acc1 += term1;
+                }
+                acc0 += (float)g; acc1 += (float)g;
+                if (acc0 < s_tau[ql0]) {
+                    const int pos = atomicAdd(&s_cnt[ql0], 1);
+                    NABO_DEV_ASSERT(pos >= 0 && pos < CAP && ql0 >= 0 && ql0 < 32);
+                    gbuf[(size_t)ql0 * CAP + pos] = make_key(acc0, (uint32_t)(ref0 + rl0));
+                }
+                if (act1 && acc1 < s_tau[ql1]) {
+                    const int pos = atomicAdd(&s_cnt[ql1], 1);
+                    NABO_DEV_ASSERT(pos >= 0 && pos < CAP && ql1 >= 0 && ql1 < 32);
+                    gbuf[(size_t)ql1 * CAP + pos] = make_key(acc1, (uint32_t)(ref0 + rl1));
+                }
+                base += 64;
+            } else {
+                const int i = base + lane;
+                const bool active = i < n;
+                const int e = active ? work[i] : 0;
+                const int ql = e >> 8, rl = e & 127;
+                const float* xb = xs + ql;
+                const float* yb = ys + (rl >> 6) * (g * 64) + (rl & 63);
+                float acc = 0.f;
+#pragma unroll 5
+                for (int k = 0; k < g; ++k) {
+                    const float x = xb[k * 32], y = yb[k * 64];
+                    const float num = fabsf(x - y), xa = fabsf(x);
+                    const float term = fmaf(num, rcp_approx(xa + (fabsf(y) + 0.01f)), -1.0f);
+                    if (num < fm * xa) acc += term;
+                }
+                acc += (float)g;
+                if (active && acc < s_tau[ql]) {
+                    const int pos = atomicAdd(&s_cnt[ql], 1);
+                    NABO_DEV_ASSERT(pos >= 0 && pos < CAP && ql >= 0 && ql < 32);
+                    gbuf[(size_t)ql * CAP + pos] = make_key(acc, (uint32_t)(ref0 + rl));
+                }
+                base += 32;
             }
             __syncwarp();
-            // a round adds at most 32 keys to one query: keep every buffer at or below CAP - 32.  Compacting
-            // earlier than that (kprime + trig_extra keys) keeps tau closer to the true running K'-th best
-            // score: a stale threshold lets proportionally more pairs through to the dense evaluation.
-            const int trig = min(CAP - 32, kprime + p.trig_extra);
-            unsigned need = __ballot_sync(0xffffffffu, s_cnt[lane] > trig);
-            while (need) {
-                const int src = __ffs(need) - 1;
-                need &= need - 1;
-                int nc;
-                float nt;
-                compact_select<4>(gbuf + (size_t)src * CAP, s_cnt[src], lane, kprime, trig - 4 > kprime ? trig - 4 : kprime, hist, nc, nt);
-                if (lane == src) { s_cnt[lane] = nc; s_tau[lane] = nt; }
-                __syncwarp();
-            }
+            compact_due();
         }
     };
 
@@ -371,11 +457,14 @@ sliced_kernel(const Params p) {
         s_tau[lane] = q_mine < p.n_query ? CUDART_INF_F : -CUDART_INF_F;     // padding queries reject everything
         s_cnt[lane] = 0;
         __syncwarp();
+        CBS_PROF(6)
 
         for (int jl = 0; jl < n_tiles; ++jl, ++t) {
             const int j = tile0 + jl;
             const uint32_t s = t % p.stages, use = t / p.stages;
             ptx::mbar_wait_hint(&bars->full[s], use & 1, NABO_CBS_SLEEP_NS);   // sleep, do not poll: 10 % of the issue slots went here
+            CBS_PROF_COUNT(7, 1)
+            CBS_PROF(0)
             const unsigned char* stage = smem + p.stage_off + (size_t)s * p.stage_bytes;
             const char* pl = reinterpret_cast<const char*>(stage);
             const float* ys = reinterpret_cast<const float*>(stage + plane_bytes);
@@ -394,8 +483,8 @@ sliced_kernel(const Params p) {
                     const int k = blk * 8 + d;
                     if (blk < NB - 1 || k < g) {
                         const uint32_t cw = ctrl[k >> 1];
-                        const uint32_t lo4 = (k & 1) ? ((cw >> 16) & 0xffu) : (cw & 0xffu);
-                        const uint32_t hi4 = (k & 1) ? (cw >> 24) : ((cw >> 8) & 0xffu);
+                        const uint32_t lo4 = ((k & 1) ? ((cw >> 16) & 0xffu) : (cw & 0xffu)) * 4u;
+                        const uint32_t hi4 = ((k & 1) ? (cw >> 24) : ((cw >> 8) & 0xffu)) * 4u;
                         const char* base = pl + k * (WPT * NPL * 4);
 #pragma unroll
                         for (int w = 0; w < WPT; ++w) {
@@ -440,6 +529,7 @@ sliced_kernel(const Params p) {
                 m[w] = (gt | eq) & live;
             }
 
+            CBS_PROF(1)
             // ---- survivors -> work list -> phase 2
             int mine = 0;
 #pragma unroll
@@ -464,7 +554,9 @@ sliced_kernel(const Params p) {
                         }
                     }
                     __syncwarp();
+                    CBS_PROF(2)
                     evaluate(total, ys, j * RT);
+                    CBS_PROF(3)
                 } else {
                     // dense tile (cold threshold): one byte column of one word at a time, at most 256 entries
                     for (int w = 0; w < WPT; ++w) {
@@ -490,12 +582,16 @@ sliced_kernel(const Params p) {
                                 work[pos++] = (unsigned short)((lane << 8) | (w * 32 + b));
                             }
                             __syncwarp();
+                            CBS_PROF(2)
                             evaluate(tot, ys, j * RT);
+                            CBS_PROF(3)
                         }
                     }
                 }
             }
+            CBS_PROF(2)
             release_tile(t, s);
+            CBS_PROF(5)
         }
 
         // ---- round done: exact selection of every query of this warp, emit candidates + threshold
@@ -517,10 +613,21 @@ sliced_kernel(const Params p) {
             }
         }
         __syncwarp();
+        CBS_PROF(6)
     }
+    CBS_PROF_FLUSH
 }
 
 }  // namespace cbs
+
+#ifdef NABO_CBS_PROF
+extern "C" int nabo_dbg_cbs_prof(unsigned long long* out_host, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out_host, cbs::g_cbs_prof, sizeof(unsigned long long) * 12);
+    if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(cbs::g_cbs_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 // ------------------------------------------------------------------ host side
 bool nabo_cbs_supported(int g, int k, int drop_first) {
@@ -558,7 +665,7 @@ int nabo_cbs_split(int n_query, int n_ref, int k, int drop_first) {
     const int per_cta = (n_groups + cbs_grid(1 << 30) - 1) / cbs_grid(1 << 30);
     int s = per_cta > 0 ? cbs::NW / per_cta : 1;
     if (s > NABO_CBS_MAX_SPLIT) s = NABO_CBS_MAX_SPLIT;
-    while (s > 1 && (n_tiles / s < 64 || s * nabo_cb_kprime(k, drop_first) > 128)) --s;
+    while (s > 1 && (n_tiles / s < 8192 / cbs::RT || s * nabo_cb_kprime(k, drop_first) > 128)) --s;
     return s < 1 ? 1 : s;
 }
 
