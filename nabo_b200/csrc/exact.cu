@@ -742,7 +742,12 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
         if (__any_sync(0xffffffffu, j >= 0)) n_slots = u + 1;
     }
     double accs[4] = {0.0, 0.0, 0.0, 0.0};
-    if (n_slots == 1) pair_rows<METRIC, 1>(xq, r, ldr, jj, g, f, vec2, accs);
+    if (METRIC == NABO_MOD_CANBERRA) {
+        // the FP64 division sits under a divergent branch: slot by slot, so that a slot with few lanes costs few divisions
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (u < n_slots) pair_rows<METRIC, 1>(xq, r, ldr, jj + u, g, f, vec2, accs + u);
+    } else if (n_slots == 1) pair_rows<METRIC, 1>(xq, r, ldr, jj, g, f, vec2, accs);
     else if (n_slots == 2) pair_rows<METRIC, 2>(xq, r, ldr, jj, g, f, vec2, accs);
     else if (n_slots > 2) pair_rows<METRIC, 4>(xq, r, ldr, jj, g, f, vec2, accs);
     int n_valid = 0, n_finite = 0;
