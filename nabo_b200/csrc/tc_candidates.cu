@@ -129,16 +129,22 @@ __global__ void scale_kernel(const unsigned int* __restrict__ maxq_bits, const u
     scal[3] = cosine ? 1.0 : 0.0;
 }
 
-// One thread per row; 16-byte chunk kc of row r of tile t lands at
+// PACK_SPLIT threads per row (thread c takes the 16-byte chunks kc = c, c + PACK_SPLIT, ...); chunk kc of row r of
+// tile t lands at
 //   t * TILE*kp*2 + kc * (TILE*16) + (r>>3)*128 + (r&7)*16
-// (core matrices of 8 rows x 16 B, K-chunk-major: SBO = 128 B, LBO = TILE*16 B).
+// (core matrices of 8 rows x 16 B, K-chunk-major: SBO = 128 B, LBO = TILE*16 B).  The chunks that hold the norm
+// columns 3g .. 3g+2 of a reference row need the whole ||r~||^2: they are written after the partial sums of the
+// row's threads have met in shared memory (fixed order: deterministic).
 // perm (or NULL): packed row i holds input row perm[i] (locality order, see order_* below)
+constexpr int PACK_SPLIT = 4;
 template <bool IS_QUERY>
-__global__ void __launch_bounds__(TILE)
+__global__ void __launch_bounds__(TILE * PACK_SPLIT)
 pack_kernel(const double* __restrict__ x, int ld, int n, int g, int kp, const double* __restrict__ norms2,
             const double* __restrict__ scal, const uint8_t* __restrict__ mask, const uint32_t* __restrict__ perm,
             __half* __restrict__ out, double* __restrict__ qn2_out) {
-    const int r = threadIdx.x;
+    __shared__ double part[PACK_SPLIT][TILE];
+    const int r = threadIdx.x & (TILE - 1);
+    const int c = threadIdx.x / TILE;                 // warp-uniform
     const long long prow = (long long)blockIdx.x * TILE + r;
     __half* tile = out + (size_t)blockIdx.x * TILE * kp;
     const bool live = prow < n;
@@ -155,9 +161,10 @@ pack_kernel(const double* __restrict__ x, int ld, int n, int g, int kp, const do
     if (!live && !IS_QUERY) dead = true;        // padding rows of the last reference tile: score 60000, like a masked
                                                 // cell, so the epilogue needs no column-limit test
     const double* p = x + (live ? row : 0) * (long long)ld;
-    double n2 = 0.0;            // ||x~||^2 of the split value actually fed to the tensor core (scaled units)
     const int nchunks = kp / 8;
-    for (int kc = 0; kc < nchunks; ++kc) {
+    // chunk kc of this row; n2 (in/out): ||x~||^2 of the split value actually fed to the tensor core (scaled units),
+    // summed over the segment-0 columns of the chunk; n2_row: the whole row's sum, for the norm columns
+    auto chunk = [&](int kc, double& n2, double n2_row) {
         __align__(16) __half h[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -181,8 +188,8 @@ pack_kernel(const double* __restrict__ x, int ld, int n, int g, int kp, const do
             h[e] = v;
         }
         if (!IS_QUERY && (live || dead) && 3 * g + 3 > kc * 8 && 3 * g < kc * 8 + 8) {
-            // norm pieces n1 + n2 + n3 = ||r~||^2 (n2 is complete here: columns >= 3g come after segment 0)
-            double rem = dead ? 60000.0 : n2;
+            // norm pieces n1 + n2 + n3 = ||r~||^2
+            double rem = dead ? 60000.0 : n2_row;
             for (int t = 0; t < 3; ++t) {
                 const int col = 3 * g + t;
                 const __half piece = __double2half(rem);
@@ -193,8 +200,39 @@ pack_kernel(const double* __restrict__ x, int ld, int n, int g, int kp, const do
         }
         *reinterpret_cast<uint4*>(reinterpret_cast<char*>(tile) + (size_t)kc * (TILE * 16) + (r >> 3) * 128 + (r & 7) * 16) =
             *reinterpret_cast<const uint4*>(h);
+    };
+    const int norm_lo = (3 * g) / 8, norm_hi = (3 * g + 2) / 8;        // chunks that hold the norm columns
+    double n2 = 0.0;
+    for (int kc = c; kc < nchunks; kc += PACK_SPLIT) {
+        if (!IS_QUERY && kc >= norm_lo && kc <= norm_hi) continue;
+        chunk(kc, n2, 0.0);
     }
-    if (IS_QUERY && live && qn2_out) qn2_out[row] = n2;
+    if (!IS_QUERY) {
+        // segment-0 columns inside the deferred chunks (only when 3g < 8, i.e. g <= 2) still belong to the sum
+        for (int kc = norm_lo + c; kc <= norm_hi && kc < nchunks; kc += PACK_SPLIT)
+            for (int e = 0; e < 8; ++e) {
+                const int col = kc * 8 + e;
+                if (live && col < g) {
+                    const double xv = p[col] * mul;
+                    const __half hi = __double2half(xv);
+                    const __half lo = __double2half(xv - (double)__half2float(hi));
+                    const double t = (double)__half2float(hi) + (double)__half2float(lo);
+                    n2 = fma(t, t, n2);
+                }
+            }
+    }
+    part[c][r] = n2;
+    __syncthreads();
+    double n2_row = part[0][r];
+#pragma unroll
+    for (int i = 1; i < PACK_SPLIT; ++i) n2_row += part[i][r];
+    if (!IS_QUERY) {
+        for (int kc = norm_lo + c; kc <= norm_hi && kc < nchunks; kc += PACK_SPLIT) {
+            double unused = 0.0;
+            chunk(kc, unused, n2_row);
+        }
+    }
+    if (IS_QUERY && c == 0 && live && qn2_out) qn2_out[row] = n2_row;
 }
 
 // ------------------------------------------------------------------ locality order
@@ -981,8 +1019,8 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     tc::norms_kernel<<<(n_query + 255) / 256, 256, 0, st>>>(q, ldq, n_query, g, qnorm, maxbits);
     tc::norms_kernel<<<(n_ref + 255) / 256, 256, 0, st>>>(r, ldr, n_ref, g, rnorm, maxbits + 1);
     tc::scale_kernel<<<1, 1, 0, st>>>(maxbits, maxbits + 1, metric == NABO_COSINE ? 1 : 0, scal);
-    tc::pack_kernel<true><<<n_qtiles, tc::TILE, 0, st>>>(q, ldq, n_query, g, kp, qnorm, scal, nullptr, perm_q, qa, qn2);
-    tc::pack_kernel<false><<<n_rtiles, tc::TILE, 0, st>>>(r, ldr, n_ref, g, kp, rnorm, scal, mask, perm_r, rb, nullptr);
+    tc::pack_kernel<true><<<n_qtiles, tc::TILE * tc::PACK_SPLIT, 0, st>>>(q, ldq, n_query, g, kp, qnorm, scal, nullptr, perm_q, qa, qn2);
+    tc::pack_kernel<false><<<n_rtiles, tc::TILE * tc::PACK_SPLIT, 0, st>>>(r, ldr, n_ref, g, kp, rnorm, scal, mask, perm_r, rb, nullptr);
     NABO_LAUNCH_CHECK("tc pack kernels");
     tm.end(3);
 
