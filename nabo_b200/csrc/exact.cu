@@ -692,29 +692,65 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
     nabo_route_row(route, qi, k, out_idx, out_dist, oi, od);
     double* d = smem + (size_t)warp * capp;
     int* ix = (int*)(smem + (size_t)4 * capp) + (size_t)warp * capp;
+    const size_t hist_off = (size_t)6 * capp + (size_t)4 * xs_dims;      // FROM_BUF only: 256 counters per warp
     const double* x = q + (long long)qi * ldq;
     double nq = 0.0;
     if (METRIC == NABO_COSINE) nq = seq_sqnorm(x, g);
     // FROM_BUF: final K' selection of the query's candidate buffer (what tc::emit_kernel does otherwise): the 128
     // keys are sorted by score in registers, element u * 32 + lane of the sorted list ends up in kpl[u]
-    uint32_t ks[4], kpl[4];
+    // FROM_BUF: final K' selection of the query's candidate buffer (what tc::emit_kernel does otherwise).  One
+    // histogram pass over the scores finds a cut with at least K' keys at or below it; they all become candidates
+    // (a few more than K', at most 2 slots per lane) and the threshold is the largest kept score: everything else
+    // in the buffer lies in a higher bin.  If the cut keeps more than min(64, capp) keys (ties), the 128 keys are sorted by
+    // score in registers instead and exactly K' are taken.  Either way the list ends up in ix[0 .. nc).
     int nc = 0;
     float tau_q = CUDART_INF_F;
     if (FROM_BUF) {
         const int n = cb.cnt[qi];
         const unsigned long long* gb = cb.buf + (size_t)qi * sel::CAP;
+        float fv[4];
+        uint32_t kpl[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = u * 32 + lane;
             const unsigned long long kv = i < n ? __ldcg(gb + i) : 0ull;
-            ks[u] = i < n ? float_to_sortable(__uint_as_float((uint32_t)(kv >> 32))) : 0xffffffffu;
+            fv[u] = __uint_as_float((uint32_t)(kv >> 32));
             kpl[u] = (uint32_t)kv;
         }
-        sel::sortn<4>(ks, kpl, lane);
-        nc = n < cb.kprime ? n : cb.kprime;
-        const int e = cb.kprime - 1;                      // kprime <= 64
-        const uint32_t ts = __shfl_sync(0xffffffffu, (e >> 5) ? ks[1] : ks[0], e & 31);
-        tau_q = n >= cb.kprime ? sortable_to_float(ts) : cb.tau[qi];
+        uint32_t* hist = reinterpret_cast<uint32_t*>(smem + hist_off) + warp * 256;
+        int bin[4], cut_bin, kept;
+        bool reach;
+        sel::histogram_cut<4>(fv, n, lane, cb.kprime, hist, bin, cut_bin, kept, reach);
+        if (kept <= (capp < 64 ? capp : 64)) {       // the list must fit the warp's capp slots
+            int base = 0;
+            float tmax = -CUDART_INF_F;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool keep = u * 32 + lane < n && bin[u] <= cut_bin;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) {
+                    ix[base + __popc(m & ((1u << lane) - 1u))] = (int)kpl[u];
+                    tmax = fmaxf(tmax, fv[u]);
+                }
+                base += __popc(m);
+            }
+            tmax = sortable_to_float(__reduce_max_sync(0xffffffffu, float_to_sortable(tmax)));
+            nc = kept;
+            tau_q = reach ? tmax : cb.tau[qi];
+        } else {
+            uint32_t ks[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ks[u] = u * 32 + lane < n ? float_to_sortable(fv[u]) : 0xffffffffu;
+            sel::sortn<4>(ks, kpl, lane);
+            nc = cb.kprime;                                   // n >= kept > capp >= kprime here
+            const int e = cb.kprime - 1;                      // kprime <= 64
+            const uint32_t ts = __shfl_sync(0xffffffffu, (e >> 5) ? ks[1] : ks[0], e & 31);
+            tau_q = sortable_to_float(ts);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (u * 32 + lane < nc) ix[u * 32 + lane] = (int)kpl[u];
+        }
+        __syncwarp();
     } else if (cert.kind != NABO_CERT_NONE) {
         tau_q = cert.tau[qi];
     }
@@ -734,7 +770,7 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
         const int c = u * 32 + lane;
         int j = -1;
         if (u * 32 < capp) {
-            if (FROM_BUF) j = (u < 2 && c < nc) ? (int)kpl[u] : -1;
+            if (FROM_BUF) j = (u < 2 && c < nc) ? ix[c] : -1;
             else j = c < n_cand ? cand[(long long)qi * n_cand + c] : -1;
         }
         if (!(j >= 0 && j < n_ref)) j = -1;
@@ -830,6 +866,7 @@ int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n
     size_t smem = (size_t)4 * capp * (sizeof(double) + sizeof(int));
     const int xs_dims = g <= 1024 ? g : 0;                 // the query rides in shared memory when it is short enough
     smem += (size_t)4 * xs_dims * sizeof(double);
+    if (from_buf) smem += (size_t)4 * 256 * sizeof(uint32_t);
     const bool vec2 = ((uintptr_t)r & 15) == 0 && (ldr & 1) == 0;
     dim3 grid((n_query + 3) / 4);
     NaboCandBuf cb;

@@ -191,4 +191,60 @@ static __device__ __noinline__ void compact_select(unsigned long long* gbuf, int
     __syncwarp();
 }
 
+// The histogram cut of compact_select on keys already in registers: bin[u] of every live key and the cut bin with
+// at least kprime keys at or below it (kept = how many).  reach = false when n < kprime (keep everything).
+// fv[u] of element i = u * 32 + lane, live iff i < n.  hist: 256 counters of this warp in shared memory.
+template <int KPL>
+__device__ __forceinline__ void histogram_cut(const float (&fv)[KPL], int n, int lane, int kprime, uint32_t* hist,
+                                              int (&bin)[KPL], int& cut_bin, int& kept, bool& reach_out) {
+    float flo = CUDART_INF_F, fhi = -CUDART_INF_F;
+#pragma unroll
+    for (int u = 0; u < KPL; ++u)
+        if (u * 32 + lane < n) { flo = fminf(flo, fv[u]); fhi = fmaxf(fhi, fv[u]); }
+    flo = sortable_to_float(__reduce_min_sync(0xffffffffu, float_to_sortable(flo)));
+    fhi = sortable_to_float(__reduce_max_sync(0xffffffffu, float_to_sortable(fhi)));
+    reinterpret_cast<uint4*>(hist)[lane * 2] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(hist)[lane * 2 + 1] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    const float range = fhi - flo;
+    const float scale = range > 0.f ? 255.999f / range : 0.f;
+#pragma unroll
+    for (int u = 0; u < KPL; ++u) {
+        bin[u] = max(0, min(255, (int)((fv[u] - flo) * scale)));
+        if (u * 32 + lane < n) atomicAdd(&hist[bin[u]], 1u);
+    }
+    __syncwarp();
+    const uint4 h0 = reinterpret_cast<const uint4*>(hist)[lane * 2];
+    const uint4 h1 = reinterpret_cast<const uint4*>(hist)[lane * 2 + 1];
+    const uint32_t c[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    uint32_t mine = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mine += c[e];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const unsigned reach = __ballot_sync(0xffffffffu, incl >= (uint32_t)kprime);
+    cut_bin = 255;
+    kept = n;
+    reach_out = reach != 0;
+    if (reach) {
+        const int owner = __ffs(reach) - 1;
+        uint32_t run = incl - mine;
+        int b = 7;
+        uint32_t k_at = 0;
+        bool found = false;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            run += c[e];
+            if (!found && run >= (uint32_t)kprime) { found = true; b = e; k_at = run; }
+        }
+        cut_bin = __shfl_sync(0xffffffffu, lane * 8 + b, owner);
+        kept = (int)__shfl_sync(0xffffffffu, k_at, owner);
+    }
+    __syncwarp();
+}
+
 }  // namespace sel

@@ -45,6 +45,23 @@ def test_fast_self_knn_with_duplicates(core):
     assert same_bits(fd[:300], od) and np.array_equal(fi[:300], oi)
 
 
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_fast_tie_class_larger_than_the_rerank_width(core, metric):
+    """100 identical reference cells that are the nearest neighbours of a block of queries: the final histogram cut
+    of the fused re-rank keeps more than its 64 slots, the sort path takes over, the certificate fails on the tie
+    and the exact engine answers - index order inside the tie class."""
+    from nabo_b200 import synth
+    r = synth.pc_mixture(9000, 50, seed=11)
+    q = synth.pc_mixture(700, 50, seed=12)
+    r[2000:2100] = r[2000]
+    q[50:90] = r[2000] * (1.0 + 1e-9)
+    fi, fd, st = core.knn(q, r, 30, metric, mode="fast", return_stats=True)
+    ei, ed = core.knn(q, r, 30, metric, mode="exact")
+    assert same_bits(fd, ed) and np.array_equal(fi, ei)
+    assert (fi[50:90] == np.arange(2000, 2030)[None, :]).all()
+    assert 40 <= st["rows_exact_fallback"] < 100
+
+
 def test_fast_mask_nan_offset(core):
     from nabo_b200 import synth
     q = synth.pc_mixture(700, 30, seed=101)
