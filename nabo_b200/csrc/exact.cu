@@ -615,6 +615,15 @@ int nabo_knn_exact_launch_ex(const double* q, int ldq, const double* r, int ldr,
     return 0;
 }
 
+#ifndef NABO_RR_HIST
+#define NABO_RR_HIST 1         // development switches of the re-rank kernel (A/B builds)
+#endif
+#ifndef NABO_RR_SCRAMBLE
+#define NABO_RR_SCRAMBLE 1
+#endif
+#ifndef NABO_RR_FUSED
+#define NABO_RR_FUSED 1
+#endif
 // ------------------------------------------------------------------ exact re-rank of candidates
 // One warp per query.  cand (n_query x n_cand) holds LOCAL reference indices, -1 = empty,
 // all distinct.  With a certificate (NaboCert.kind != 0) the kernel also proves that no
@@ -675,6 +684,15 @@ __device__ __forceinline__ void pair_rows(const double* __restrict__ x, const do
     for (int u = 0; u < NU; ++u) acc[u] = a[u];
 }
 
+#ifdef NABO_RR_STATS      // development counters: [0] rows [1] rows on the sort path [2] sum of cut-bin sizes [3] sum of buffer
+__device__ unsigned long long g_rr_stats[8];   // counts [4] sum of keys ranked away
+extern "C" int nabo_dbg_rr_stats(unsigned long long* out_host, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out_host, g_rr_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_rr_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 template <int METRIC, bool FROM_BUF>
 __global__ void __launch_bounds__(128)
 rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ r, int ldr, int n_query,
@@ -699,10 +717,10 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
     // FROM_BUF: final K' selection of the query's candidate buffer (what tc::emit_kernel does otherwise): the 128
     // keys are sorted by score in registers, element u * 32 + lane of the sorted list ends up in kpl[u]
     // FROM_BUF: final K' selection of the query's candidate buffer (what tc::emit_kernel does otherwise).  One
-    // histogram pass over the scores finds a cut with at least K' keys at or below it; they all become candidates
-    // (a few more than K', at most 2 slots per lane) and the threshold is the largest kept score: everything else
-    // in the buffer lies in a higher bin.  If the cut keeps more than min(64, capp) keys (ties), the 128 keys are sorted by
-    // score in registers instead and exactly K' are taken.  Either way the list ends up in ix[0 .. nc).
+    // histogram pass over the scores finds the bin that holds the K'-th best key; the keys of lower bins and the best
+    // of that bin (ranked by pairwise comparison) are the K' candidates, the threshold is the largest kept score.
+    // If the cut bin holds more than 48 keys (a big tie class), the 128 keys are sorted by score in registers
+    // instead.  Either way the list ends up in ix[0 .. nc), nc <= K' <= capp.
     int nc = 0;
     float tau_q = CUDART_INF_F;
     if (FROM_BUF) {
@@ -721,12 +739,39 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
         int bin[4], cut_bin, kept;
         bool reach;
         sel::histogram_cut<4>(fv, n, lane, cb.kprime, hist, bin, cut_bin, kept, reach);
-        if (kept <= (capp < 64 ? capp : 64)) {       // the list must fit the warp's capp slots
+        // keys of the cut bin beyond the K' needed: ranked among themselves (score, then buffer position), so that
+        // exactly K' stay - every extra candidate is a 400-byte row gather from HBM once the reference outgrows L2
+        const int c_cut = reach ? (int)hist[cut_bin] : 0;
+        const int need = cb.kprime - (kept - c_cut);             // keys still wanted from the cut bin: 1 .. c_cut
+#ifdef NABO_RR_STATS
+        if (lane == 0) {
+            atomicAdd(&g_rr_stats[0], 1ull); atomicAdd(&g_rr_stats[1], (unsigned long long)(reach && c_cut > 48));
+            atomicAdd(&g_rr_stats[2], (unsigned long long)c_cut); atomicAdd(&g_rr_stats[3], (unsigned long long)n);
+            atomicAdd(&g_rr_stats[4], (unsigned long long)(reach ? c_cut - need : 0));
+        }
+#endif
+        if (NABO_RR_HIST && (!reach || c_cut <= 48)) {
+            int rank[4] = {0, 0, 0, 0};
+            if (reach && c_cut > need) {
+#pragma unroll
+                for (int us = 0; us < 4; ++us) {
+                    unsigned mm = __ballot_sync(0xffffffffu, us * 32 + lane < n && bin[us] == cut_bin);
+                    while (mm) {
+                        const int src = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const float sv = __shfl_sync(0xffffffffu, fv[us], src);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            rank[u] += (sv < fv[u] || (sv == fv[u] && us * 32 + src < u * 32 + lane)) ? 1 : 0;
+                    }
+                }
+                kept = cb.kprime;
+            }
             int base = 0;
             float tmax = -CUDART_INF_F;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const bool keep = u * 32 + lane < n && bin[u] <= cut_bin;
+                const bool keep = u * 32 + lane < n && (bin[u] < cut_bin || (bin[u] == cut_bin && rank[u] < need));
                 const unsigned m = __ballot_sync(0xffffffffu, keep);
                 if (keep) {
                     ix[base + __popc(m & ((1u << lane) - 1u))] = (int)kpl[u];
@@ -742,10 +787,10 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
 #pragma unroll
             for (int u = 0; u < 4; ++u) ks[u] = u * 32 + lane < n ? float_to_sortable(fv[u]) : 0xffffffffu;
             sel::sortn<4>(ks, kpl, lane);
-            nc = cb.kprime;                                   // n >= kept > capp >= kprime here
+            nc = n < cb.kprime ? n : cb.kprime;
             const int e = cb.kprime - 1;                      // kprime <= 64
             const uint32_t ts = __shfl_sync(0xffffffffu, (e >> 5) ? ks[1] : ks[0], e & 31);
-            tau_q = sortable_to_float(ts);
+            tau_q = n >= cb.kprime ? sortable_to_float(ts) : cb.tau[qi];
 #pragma unroll
             for (int u = 0; u < 2; ++u)
                 if (u * 32 + lane < nc) ix[u * 32 + lane] = (int)kpl[u];
@@ -765,12 +810,20 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
     const double* xq = xw ? xw : x;
     int jj[4];
     int n_slots = 0;
+    const bool scramble = NABO_RR_SCRAMBLE && (long long)n_ref * ldr * 8 > (96ll << 20);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int c = u * 32 + lane;
         int j = -1;
         if (u * 32 < capp) {
-            if (FROM_BUF) j = (u < 2 && c < nc) ? ix[c] : -1;
+            if (FROM_BUF) {
+                // list positions are dealt to the lanes through a fixed bijection of [0, capp): in list order (the
+                // order the sweep found them = ascending reference row) the row gathers of a warp run measurably
+                // slower once the reference outgrows L2 (2.9 vs 2.3 ms at 227 k x 1.25 M); an L2-resident reference
+                // prefers the list order (0.46 vs 0.49 ms at 100 k x 100 k)
+                const int cpos = scramble ? ((c * 27 + 5) & (capp - 1)) : c;
+                j = (u < 2 && cpos < nc) ? ix[cpos] : -1;
+            }
             else j = c < n_cand ? cand[(long long)qi * n_cand + c] : -1;
         }
         if (!(j >= 0 && j < n_ref)) j = -1;
@@ -778,7 +831,7 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
         if (__any_sync(0xffffffffu, j >= 0)) n_slots = u + 1;
     }
     double accs[4] = {0.0, 0.0, 0.0, 0.0};
-    if (METRIC == NABO_MOD_CANBERRA) {
+    if (METRIC == NABO_MOD_CANBERRA || !NABO_RR_FUSED) {
         // the FP64 division sits under a divergent branch: slot by slot, so that a slot with few lanes costs few divisions
 #pragma unroll
         for (int u = 0; u < 4; ++u)
