@@ -56,6 +56,9 @@ constexpr int MAX_KPRIME = 96;      // K' lists go to the re-rank, which takes a
 #ifndef NABO_TC_SLEEP_NS
 #define NABO_TC_SLEEP_NS 2000        // suspend-time hint of the producer's mbarrier waits (0 = plain polling)
 #endif
+#ifndef NABO_TC_EPI_SLEEP_NS
+#define NABO_TC_EPI_SLEEP_NS 0       // suspend-time hint of the epilogue warps' wait for an accumulator (0 = plain polling)
+#endif
 #ifndef NABO_TC_UNIFORM_HIT
 #define NABO_TC_UNIFORM_HIT 0
 #endif
@@ -687,7 +690,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
 #endif
                 const uint32_t taddr0 = tlane0 + buf * TILE;
                 TC_CLK(t_w);
+#if NABO_TC_EPI_SLEEP_NS
+                ptx::mbar_wait_hint(&bars->acc_full[buf], acc_par, NABO_TC_EPI_SLEEP_NS);
+#else
                 ptx::mbar_wait(&bars->acc_full[buf], acc_par);
+#endif
                 ptx::tc_fence_after();
                 TC_CLK_ADD(7, t_w);
                 const int jt = sweep_tile(j, start, p.n_rtiles);  // the reference tile this sweep position holds
