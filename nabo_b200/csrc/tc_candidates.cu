@@ -1044,6 +1044,10 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     }
     p.a_off = pl.a_off; p.b_off = pl.b_off; p.sort_off = pl.sort_off; p.bar_off = pl.bar_off;
     p.soft = tc::CAP - tc::CHUNK - 16 > kprime ? tc::CAP - tc::CHUNK - 16 : kprime;
+    {
+        const char* e = getenv("NABO_TC_SOFT");      // development: compaction trigger (keys in the buffer at a tile end)
+        if (e && atoi(e) >= kprime + 8 && atoi(e) <= tc::CAP - tc::CHUNK) p.soft = atoi(e);
+    }
 #define NABO_TC_LAUNCH1(KS, MD)                                                                                    \
     do {                                                                                                           \
         NABO_CUDA(cudaFuncSetAttribute(tc::candidates_kernel<KS, MD>,                                              \
