@@ -700,10 +700,10 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
               int idx_offset, const int32_t* __restrict__ cand, int n_cand, int capp, const NaboCert cert,
               int* __restrict__ fail_rows, int* __restrict__ fail_count,
               int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const NaboRoute route,
-              const NaboCandBuf cb, int xs_dims, bool vec2) {
+              const NaboCandBuf cb, int xs_dims, bool vec2, int row0) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int qi = blockIdx.x * 4 + warp;
+    const int qi = row0 + blockIdx.x * 4 + warp;
     if (qi >= n_query) return;
     int32_t* oi;
     double* od;
@@ -724,7 +724,7 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
     int nc = 0;
     float tau_q = CUDART_INF_F;
     if (FROM_BUF) {
-        const int n = cb.cnt[qi];
+        const int n = __ldcg(cb.cnt + qi);            // through L2: the producer may still be running (dependent launch)
         const unsigned long long* gb = cb.buf + (size_t)qi * sel::CAP;
         float fv[4];
         uint32_t kpl[4];
@@ -781,7 +781,7 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
             }
             tmax = sortable_to_float(__reduce_max_sync(0xffffffffu, float_to_sortable(tmax)));
             nc = kept;
-            tau_q = reach ? tmax : cb.tau[qi];
+            tau_q = reach ? tmax : __ldcg(cb.tau + qi);
         } else {
             uint32_t ks[4];
 #pragma unroll
@@ -790,7 +790,7 @@ rerank_kernel(const double* __restrict__ q, int ldq, const double* __restrict__ 
             nc = n < cb.kprime ? n : cb.kprime;
             const int e = cb.kprime - 1;                      // kprime <= 64
             const uint32_t ts = __shfl_sync(0xffffffffu, (e >> 5) ? ks[1] : ks[0], e & 31);
-            tau_q = n >= cb.kprime ? sortable_to_float(ts) : cb.tau[qi];
+            tau_q = n >= cb.kprime ? sortable_to_float(ts) : __ldcg(cb.tau + qi);
 #pragma unroll
             for (int u = 0; u < 2; ++u)
                 if (u * 32 + lane < nc) ix[u * 32 + lane] = (int)kpl[u];
@@ -910,10 +910,11 @@ int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n
                        int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                        const int32_t* cand, int n_cand, const NaboCert& cert, int* fail_rows, int* fail_count,
                        int32_t* out_idx, double* out_dist, const NaboRoute& route, cudaStream_t st,
-                       const NaboCandBuf* from_buf) {
+                       const NaboCandBuf* from_buf, int row0, bool dependent) {
     NABO_ARG(n_cand >= 1 && n_cand <= 128, "rerank: n_cand=%d unsupported (1..128)", n_cand);
     NABO_ARG(k >= 1 && k + (drop_first ? 1 : 0) <= n_cand, "rerank: k=%d does not fit n_cand=%d", k, n_cand);
-    if (n_query == 0) return 0;
+    NABO_ARG(row0 >= 0 && row0 <= n_query, "rerank: row0=%d outside [0, %d]", row0, n_query);
+    if (n_query - row0 == 0) return 0;
     int capp = nabo_next_pow2(n_cand);
     if (capp < 32) capp = 32;
     size_t smem = (size_t)4 * capp * (sizeof(double) + sizeof(int));
@@ -921,7 +922,7 @@ int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n
     smem += (size_t)4 * xs_dims * sizeof(double);
     if (from_buf) smem += (size_t)4 * 256 * sizeof(uint32_t);
     const bool vec2 = ((uintptr_t)r & 15) == 0 && (ldr & 1) == 0;
-    dim3 grid((n_query + 3) / 4);
+    dim3 grid((n_query - row0 + 3) / 4);
     NaboCandBuf cb;
     cb.buf = nullptr; cb.cnt = nullptr; cb.tau = nullptr; cb.kprime = 0;
     if (from_buf) {
@@ -929,15 +930,26 @@ int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n
                  "rerank: buffer mode needs K' = n_cand <= 64");
         cb = *from_buf;
     }
+    // dependent launch: the kernel may start as soon as every CTA of the kernel in front of it on the stream has executed
+    // griddepcontrol.launch_dependents (it never calls griddepcontrol.wait: what it reads was fenced before the signal)
+    // (measured at config 2: letting these blocks share the busy SMs - one fits next to a candidate-kernel CTA - costs
+    // that kernel 0.14 ms and hides 0.24 ms; a 16 KB shared-memory request that keeps them on the idle SMs only is
+    // slower, the re-rank then outlasts the last wave)
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = grid; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = dependent ? 1 : 0;
 #define LAUNCH(M)                                                                                              \
     if (from_buf)                                                                                              \
-        rerank_kernel<M, true><<<grid, 128, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask,         \
-                                                        drop_first, idx_offset, cand, n_cand, capp, cert,      \
-                                                        fail_rows, fail_count, out_idx, out_dist, route, cb, xs_dims, vec2);  \
+        NABO_CUDA(cudaLaunchKernelEx(&cfg, rerank_kernel<M, true>, q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, \
+                                     drop_first, idx_offset, cand, n_cand, capp, cert, fail_rows, fail_count,  \
+                                     out_idx, out_dist, route, cb, xs_dims, vec2, row0));                      \
     else                                                                                                       \
-        rerank_kernel<M, false><<<grid, 128, smem, st>>>(q, ldq, r, ldr, n_query, n_ref, g, k, f, mask,        \
-                                                         drop_first, idx_offset, cand, n_cand, capp, cert,     \
-                                                         fail_rows, fail_count, out_idx, out_dist, route, cb, xs_dims, vec2);
+        NABO_CUDA(cudaLaunchKernelEx(&cfg, rerank_kernel<M, false>, q, ldq, r, ldr, n_query, n_ref, g, k, f, mask, \
+                                     drop_first, idx_offset, cand, n_cand, capp, cert, fail_rows, fail_count,  \
+                                     out_idx, out_dist, route, cb, xs_dims, vec2, row0));
     if (metric == NABO_EUCLIDEAN) { LAUNCH(NABO_EUCLIDEAN) }
     else if (metric == NABO_MOD_CANBERRA) { LAUNCH(NABO_MOD_CANBERRA) }
     else if (metric == NABO_COSINE) { LAUNCH(NABO_COSINE) }

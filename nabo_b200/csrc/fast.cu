@@ -110,21 +110,37 @@ int nabo_knn_fast(const double* q, int ldq, const double* r, int ldr, int n_quer
     raw.buf = nullptr;
     int n_split = nabo_tc_split(n_query, n_ref);              // > 1 only when there are fewer query items than SMs
     while (n_split > 1 && n_split * nabo_tc_kprime(k, drop_first) > 128) --n_split;     // the re-rank takes <= 128 candidates
-    int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, mask, drop_first, &n_split, ar, &cand,
-                                &kprime, &tau, &qn2, &scal, &launches, tm, st, &raw);  // n_split out: K' lists per query
-    if (rc) return rc;
+    // the failure list first: the re-rank of the full waves may start while the candidate pass is still running
     int* fail_rows = ar.take<int>(n_query);
     int* fail_count = ar.take<int>(1);
     char* split_ws = ar.take<char>(nabo_exact_split_workspace(k + (drop_first ? 1 : 0)));
     if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
     NABO_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
+    NaboTailSplit tail;
+    tail.rows_full = 0; tail.applies = 0;
+    tail.dry = stats_host != nullptr;      // stage timing asked for: the candidate kernel is timed on its own
+    int rc = nabo_tc_candidates(q, ldq, r, ldr, n_query, n_ref, g, k, metric, mask, drop_first, &n_split, ar, &cand,
+                                &kprime, &tau, &qn2, &scal, &launches, tm, st, &raw, &tail);  // n_split out: K' lists per query
+    if (rc) return rc;
+    if (!ar.ok) return nabo_set_error(NABO_EWORKSPACE, "knn: workspace too small");
     NaboCert cert;
     cert.kind = metric == NABO_COSINE ? NABO_CERT_COSINE : NABO_CERT_EUCLID;
     cert.tau = tau; cert.qn2 = qn2; cert.scal = scal; cert.c_acc = kCAcc;
     cert.abs_slack = 2.0 * sqrt((double)g) * 5.9604644775390625e-08;
+    int row0 = 0;
+    if (tail.rows_full > 0) {
+        // queries of the full waves: their re-rank is a dependent launch right behind the candidate kernel and runs
+        // under its last, partly filled wave
+        rc = nabo_rerank_launch(q, ldq, r, ldr, tail.rows_full, n_ref, g, k, metric, f, mask, drop_first, idx_offset, cand,
+                                kprime * n_split, cert, fail_rows, fail_count, out_idx, out_dist, route, st, &raw, 0, true);
+        if (rc) return rc;
+        tm.end(0);
+        row0 = tail.rows_full;
+    }
+    launches += tail.applies;
     rc = nabo_rerank_launch(q, ldq, r, ldr, n_query, n_ref, g, k, metric, f, mask, drop_first, idx_offset, cand,
                             kprime * n_split, cert, fail_rows, fail_count, out_idx, out_dist, route, st,
-                            raw.buf ? &raw : nullptr);
+                            raw.buf ? &raw : nullptr, row0);
     if (rc) return rc;
     tm.end(1);
     // rows the certificate did not clear: exact brute force (grid sized for the worst case,

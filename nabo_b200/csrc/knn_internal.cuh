@@ -83,11 +83,24 @@ struct NaboCandBuf {
     const float* tau;                // [n_query] running threshold at the end of the sweep
     int kprime;
 };
+// row0: the launch covers the queries [row0, n_query) (all pointers are those of row 0); dependent: launched with
+// programmatic stream serialisation behind a kernel that signals (NaboTailSplit)
 int nabo_rerank_launch(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, double f, const uint8_t* mask, int drop_first, int idx_offset,
                        const int32_t* cand, int n_cand, const NaboCert& cert, int* fail_rows, int* fail_count,
                        int32_t* out_idx, double* out_dist, const NaboRoute& route, cudaStream_t st,
-                       const NaboCandBuf* from_buf = nullptr);
+                       const NaboCandBuf* from_buf = nullptr, int row0 = 0, bool dependent = false);
+
+// Partly filled last wave of the persistent candidate kernel (tc_candidates.cu): every CTA executes
+// griddepcontrol.launch_dependents once its full-wave items are done, so a kernel launched right behind it on the same
+// stream with programmatic stream serialisation - the re-rank of the first rows_full queries - runs while the last wave is
+// still busy, on the SMs that wave leaves idle.  rows_full = 0: nothing to overlap.  When rows_full > 0 the candidate pass
+// has NOT closed its timing stage: the caller does, after the dependent launch.
+struct NaboTailSplit {
+    int dry;                   // in: 1 = only report (the per-stage timing pass measures the candidate kernel alone)
+    int rows_full;             // out: queries the dependent launch may take (0 with dry)
+    int applies;               // out: 1 when the shape qualifies (with or without dry)
+};
 
 struct NaboStageTimer;
 bool nabo_tc_supported(int g, int k, int drop_first);
@@ -98,7 +111,7 @@ int nabo_tc_split(int n_query, int n_ref);
 int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, const uint8_t* mask, int drop_first, int* n_split_io, NaboArena& ar, int32_t** cand_idx_out,
                        int* kprime_out, float** cert_tau_out, double** qn2_out, double** scal_out, int* launches,
-                       NaboStageTimer& tm, cudaStream_t st, NaboCandBuf* raw_out = nullptr);
+                       NaboStageTimer& tm, cudaStream_t st, NaboCandBuf* raw_out = nullptr, NaboTailSplit* tail = nullptr);
 
 bool nabo_cb_supported(int g, int k, int drop_first);
 int nabo_cb_kprime(int k, int drop_first);

@@ -327,6 +327,7 @@ struct Params {
     const __half* qa;       // packed queries  [n_qtiles_padded][TILE*kp]
     const __half* rb;       // packed references [n_rtiles][TILE*kp]
     int n_query, n_ref, kp, n_items, n_rtiles, stages, kprime, kc_out, soft;
+    int signal_round;       // MODE 0: > 0 = every CTA signals the dependent launch after its signal_round-th item (0 = never)
     int n_split;            // reference ranges per query item (work item = n_items x n_split, see nabo_tc_split)
     unsigned long long* cand_buf;   // [work item][NQ*TILE][CAP]: every (query, reference range) owns CAP keys
     int* cand_cnt;          // [work item][NQ*TILE] live keys of each buffer when its sweep ended
@@ -764,6 +765,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) candidates_kernel(const Params p)
             TC_CLK_ADD(9, t_e);
             TC_CLK_ADD(10, t_item);
             TC_FLUSH;
+            if (MODE == 0 && p.signal_round == wr + 1) {
+                // the full waves are done on this CTA: its buffers, counts and thresholds are in global memory
+                // (fence), the 12 epilogue warps meet on a named barrier, one thread lets the dependent grid - the
+                // re-rank of those queries - start while the last, partly filled wave is still running
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
+                if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+            }
         }
     }
     ptx::tc_fence_before();
@@ -866,6 +875,16 @@ static bool nabo_tc_order_enabled() {
 // (tests/test_gpu_tc.py::test_balanced_last_wave_equals_exact) but not a gain - at 100 k x 100 k the pieces start with
 // a cold threshold (candidate kernel 3.79 -> 4.24 ms) and the re-rank walks three K' lists per query (0.87 -> 1.43 ms);
 // at 200 k x 1.25 M the kernel gains 3 % and the re-rank loses as much.  Off by default.
+// NABO_TC_TAIL_OVERLAP=0 keeps the candidate pass one launch (no re-rank of the full waves under the last wave).
+static bool nabo_tc_tail_overlap_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NABO_TC_TAIL_OVERLAP");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 static bool nabo_tc_balance_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -937,7 +956,7 @@ size_t nabo_tc_workspace_bytes(int n_query, int n_ref, int g, int k, int drop_fi
 int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n_query, int n_ref, int g, int k,
                        int metric, const uint8_t* mask, int drop_first, int* n_split_io, NaboArena& ar, int32_t** cand_idx_out,
                        int* kprime_out, float** cert_tau_out, double** qn2_out, double** scal_out, int* launches,
-                       NaboStageTimer& tm, cudaStream_t st, NaboCandBuf* raw_out) {
+                       NaboStageTimer& tm, cudaStream_t st, NaboCandBuf* raw_out, NaboTailSplit* tail) {
     // raw_out != NULL: when every query has ONE buffer in input order (MODE 0, no locality order, K' <= 64, 128-key
     // buffers) the final selection is left to the re-rank kernel: raw_out is filled and no emit kernel runs.
     // *n_split_io in: reference pieces per item when there are few items (nabo_tc_split), or 0 = one piece and no
@@ -952,20 +971,20 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     const int n_rtiles = (n_ref + tc::TILE - 1) / tc::TILE;
     const int kprime = nabo_tc_kprime(k, drop_first);
     if (n_split < 1 || n_split > NABO_TC_MAX_SPLIT) n_split = 1;
-    const int grid = tc_grid(n_items * n_split);
+    const int grid_all = tc_grid(n_items * n_split);
     // MODE 2 (see work_piece): more items than CTAs, a last wave between 5 % and 90 % full, room for three K' lists
     int mode = n_split > 1 ? 1 : 0, n_full = n_items, bal_rem = 0, bal_share = 0, bal_p = 0;
-    if (mode == 0 && may_balance && n_items > grid && 3 * kprime <= 128 && n_rtiles >= 96 && nabo_tc_balance_enabled()) {
-        const int rem = n_items % grid;
-        if (rem > 0 && rem * 20 >= grid && rem * 10 <= grid * 9) {
+    if (mode == 0 && may_balance && n_items > grid_all && 3 * kprime <= 128 && n_rtiles >= 96 && nabo_tc_balance_enabled()) {
+        const int rem = n_items % grid_all;
+        if (rem > 0 && rem * 20 >= grid_all && rem * 10 <= grid_all * 9) {
             mode = 2;
             n_full = n_items - rem;
             bal_rem = rem;
-            if (rem * 2 >= grid) {                       // contiguous ranges, <= 3 pieces per item
+            if (rem * 2 >= grid_all) {                       // contiguous ranges, <= 3 pieces per item
                 bal_p = 0;
-                bal_share = (int)(((long long)rem * n_rtiles + grid - 1) / grid);
+                bal_share = (int)(((long long)rem * n_rtiles + grid_all - 1) / grid_all);
             } else {                                     // aligned pieces
-                bal_p = grid / rem < NABO_TC_MAX_SPLIT ? grid / rem : NABO_TC_MAX_SPLIT;
+                bal_p = grid_all / rem < NABO_TC_MAX_SPLIT ? grid_all / rem : NABO_TC_MAX_SPLIT;
                 bal_share = (n_rtiles + bal_p - 1) / bal_p;
             }
         }
@@ -1034,6 +1053,7 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
     tc::Params p;
     p.qa = qa; p.rb = rb;
     p.n_query = n_query; p.n_ref = n_ref; p.kp = kp; p.n_items = n_items; p.n_rtiles = n_rtiles;
+    p.signal_round = 0;
     p.stages = pl.stages; p.kprime = kprime; p.kc_out = kprime; p.n_split = n_split;
     p.n_full = n_full; p.bal_rem = bal_rem; p.bal_share = bal_share; p.bal_p = bal_p;
     p.cand_buf = cbuf; p.cand_cnt = ccnt; p.cand_tau = ctau; p.cand_idx = cand; p.cert_tau = tau;
@@ -1060,13 +1080,31 @@ int nabo_tc_candidates(const double* q, int ldq, const double* r, int ldr, int n
         else if (mode == 2) NABO_TC_LAUNCH1(KS, 2);                                                                \
         else NABO_TC_LAUNCH1(KS, 0);                                                                               \
     } while (0)
+    // Partly filled last wave (see NaboTailSplit): every CTA signals after its last full-wave item when the caller can
+    // use the gap - the fused re-rank path only (one buffer per query, input order), at least two waves, at least
+    // 16 SMs idle in the last one.
+    const bool fused = raw_out && mode == 0 && !perm_q && kprime <= 64 && tc::CAP == 128;
+    const int grid = grid_all;
+    const int rem_items = n_items % grid_all;
+    if (tail) tail->rows_full = 0, tail->applies = 0;
+    bool split_tail = tail && fused && n_items > grid_all && rem_items > 0 && grid_all - rem_items >= 16 &&
+                      nabo_tc_tail_overlap_enabled();
+    if (split_tail) {
+        tail->applies = 1;
+        if (tail->dry) split_tail = false;
+    }
+    if (split_tail) {
+        p.signal_round = n_items / grid_all;
+        tail->rows_full = (n_items - rem_items) * tc::NQ * tc::TILE;
+    }
     if (kp == 160) NABO_TC_LAUNCH(10);        // g = 50 (BASELINE configs 2-5)
     else if (kp == 80) NABO_TC_LAUNCH(5);     // g = 25 (config 1)
     else NABO_TC_LAUNCH(0);
 #undef NABO_TC_LAUNCH1
 #undef NABO_TC_LAUNCH
     NABO_LAUNCH_CHECK("candidates_kernel");
-    tm.end(0);             // the final selection below is timed with the re-rank stage
+    if (!split_tail) tm.end(0);    // the final selection below is timed with the re-rank stage; with a dependent launch the
+                                   // caller ends the stage after that launch (nothing may sit between the two kernels)
     if (raw_out) raw_out->buf = nullptr;
     if (raw_out && mode == 0 && !perm_q && kprime <= 64 && tc::CAP == 128) {
         raw_out->buf = cbuf; raw_out->cnt = ccnt; raw_out->tau = ctau; raw_out->kprime = kprime;
