@@ -14,10 +14,13 @@
 // entry is a member of A iff a probe sequence of ~1.3 loads finds it, and the row's intersection size is the
 // popcount of the warp's hit ballot (no atomics in the counting, no index arithmetic).  The gathers of 16 rows are
 // issued back to back before any of them is consumed: the kernel is bound by L2 latency, not by arithmetic.
-__device__ __forceinline__ unsigned snn_hash(int v, unsigned mask) { return (((unsigned)v * 2654435761u) >> 16) & mask; }
+// multiplicative hash, top bits: shift = 32 - log2(table size)
+__device__ __forceinline__ unsigned snn_hash(int v, int shift) { return ((unsigned)v * 2654435761u) >> shift; }
+
+constexpr int SNN_PAD = 32;      // table[tsize] mirrors table[0]: a lookup's second probe needs no wrap
 
 __global__ void __launch_bounds__(256)
-snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int tsize, const int32_t* __restrict__ ref_knn,
+snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int tsize, int shift, const int32_t* __restrict__ ref_knn,
            int n_ref, int k_ref, int k_use, const double* __restrict__ lut, uint8_t* __restrict__ counts,
            double* __restrict__ weights) {
     extern __shared__ int sm_snn[];
@@ -25,9 +28,9 @@ snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int tsize, c
     const int t = blockIdx.x * 8 + warp;
     if (t >= n_query) return;
     const int kp = (k + 31) & ~31;
-    int* table = sm_snn + warp * (tsize + 2 * kp);       // [tsize] hash table of A, -1 = empty
-    int* a_row = table + tsize;                          // [kp] the row in its own order
-    int* hits = a_row + kp;                              // [kp] per-neighbour intersection size
+    int* table = sm_snn + warp * (tsize + SNN_PAD + 2 * kp);   // [tsize (+1)] hash table of A, -1 = empty
+    int* a_row = table + tsize + SNN_PAD;                      // [kp] the row in its own order
+    int* hits = a_row + kp;                                    // [kp] per-neighbour intersection size
     const unsigned mask = (unsigned)tsize - 1u;
     for (int i = lane; i < tsize; i += 32) table[i] = -1;
     for (int i = lane; i < kp; i += 32) {
@@ -38,10 +41,10 @@ snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int tsize, c
     // insert; the warp remembers the LONGEST displacement of any key, so that a lookup is a fixed number of
     // independent probes (no data-dependent loop, no divergence): 1 + disp slots, disp is 0 or 1 at this load factor
     int disp = 0;
-    for (int i = lane; i < k; i += 32) {
+    for (int i = lane; i < kp; i += 32) {
         const int v = a_row[i];
         if (v >= 0) {
-            unsigned s_ = snn_hash(v, mask);
+            unsigned s_ = snn_hash(v, shift);
             int dd = 0;
             for (;;) {
                 const int old = atomicCAS(&table[s_], -1, v);
@@ -51,35 +54,48 @@ snn_kernel(const int32_t* __restrict__ tgt_knn, int n_query, int k, int tsize, c
             }
             disp = max(disp, dd);
         }
+        if (!(v >= 0 && v < n_ref)) a_row[i] = -1;       // from here on a_row holds the rows of ref_knn to walk
     }
     disp = __reduce_max_sync(0xffffffffu, disp);
+    __syncwarp();
+    if (lane == 0) table[tsize] = table[0];
     __syncwarp();
     // the ballot count of a row is warp-uniform: row r0 + u of a block of 16 accumulates in lane (r0 & 31) + u
     for (int c0 = 0; c0 < k_use; c0 += 32) {
         const int col = c0 + lane;
+        const bool col_ok = col < k_use;
+        const int32_t* colp = ref_knn + col;
         for (int r0 = 0; r0 < k; r0 += 16) {
-            int bv[16];
+            int bv[16];                                   // -2 = nothing to look up (never equals a key or an empty slot)
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
-                const int row = r0 + u;
-                const int j = row < k ? a_row[row] : -1;
-                bv[u] = (j >= 0 && j < n_ref && col < k_use) ? __ldg(ref_knn + (long long)j * k_ref + col) : -1;
+                const int j = a_row[r0 + u];              // r0 + u < kp
+                const int raw = (j >= 0 && col_ok) ? __ldg(colp + (size_t)j * k_ref) : -2;
+                bv[u] = raw >= 0 ? raw : -2;               // a missing neighbour (-1) must not match an empty slot
             }
             const int base = r0 & 31;
             int blk = 0;
+            if (disp <= 1) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int b = bv[u];
-                const unsigned s_ = snn_hash(b, mask);
-                bool hit;
-                if (disp <= 1) {
-                    hit = (table[s_] == b) | (table[(s_ + 1) & mask] == b);
-                } else {
-                    hit = false;
-                    for (int dd = 0; dd <= disp; ++dd) hit |= table[(s_ + dd) & mask] == b;
+                for (int u = 0; u < 16; ++u) {
+                    const int b = bv[u];
+                    const unsigned s_ = snn_hash(b, shift);
+                    const bool hit = (table[s_] == b) | (table[s_ + 1] == b);
+                    const int cnt = __popc(__ballot_sync(0xffffffffu, hit));
+                    if (lane == base + u) blk += cnt;
                 }
-                const int cnt = __popc(__ballot_sync(0xffffffffu, hit && b >= 0));
-                if (lane == base + u) blk += cnt;
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < 16; ++u) {
+                    int b = bv[0];
+#pragma unroll
+                    for (int w = 1; w < 16; ++w) b = (w == u) ? bv[w] : b;
+                    const unsigned s_ = snn_hash(b, shift);
+                    bool hit = false;
+                    for (int dd = 0; dd <= disp; ++dd) hit |= table[(s_ + dd) & mask] == b;
+                    const int cnt = __popc(__ballot_sync(0xffffffffu, hit));
+                    if (lane == base + u) blk += cnt;
+                }
             }
             const int mine = r0 + lane - base;
             if (lane >= base && lane < base + 16 && mine < k) hits[mine] += blk;
@@ -103,9 +119,10 @@ extern "C" int nabo_snn_weights(const int32_t* tgt_knn, int n_query, int k, cons
     NABO_ARG(!out_weights || lut, "snn: weights requested without a lut");
     int k_use = k < k_ref ? k : k_ref;   // ref_data[ref_c][:k], _mapping.py:193
     const int tsize = k <= 32 ? 256 : 1024;          // load factor <= 1/4: the warp walks the LONGEST probe sequence of its lanes
+    const int shift = k <= 32 ? 24 : 22;             // 32 - log2(tsize)
     const int kp = (k + 31) & ~31;
-    snn_kernel<<<(n_query + 7) / 8, 256, 8 * (tsize + 2 * kp) * sizeof(int), (cudaStream_t)stream>>>(
-        tgt_knn, n_query, k, tsize, ref_knn, n_ref, k_ref, k_use, lut, out_counts, out_weights);
+    snn_kernel<<<(n_query + 7) / 8, 256, 8 * (tsize + SNN_PAD + 2 * kp) * sizeof(int), (cudaStream_t)stream>>>(
+        tgt_knn, n_query, k, tsize, shift, ref_knn, n_ref, k_ref, k_use, lut, out_counts, out_weights);
     NABO_LAUNCH_CHECK("snn_kernel");
     return 0;
 }
