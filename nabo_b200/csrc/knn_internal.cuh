@@ -75,7 +75,7 @@ struct NaboCert {
 };
 
 // Candidates straight from the buffers the tensor-core sweep left behind (one 128-key buffer per query, query i at
-// slot i): the re-rank kernel makes the final K' selection itself (register bitonic sort) - no emit kernel, no
+// slot i): the re-rank kernel makes the final K' selection itself (histogram cut + rank inside the cut bin) - no emit kernel, no
 // candidate-index round trip.  buf == NULL: candidates come from the `cand` lists.
 struct NaboCandBuf {
     const unsigned long long* buf;   // [n_query][128] keys (score bits << 32 | reference row)
