@@ -304,6 +304,9 @@ knn_exact_kernel(const double* __restrict__ q, int ldq, const double* __restrict
                 for (int kk = 0; kk < gn; ++kk) { double v = s.ys[kk * LDS_T + threadIdx.x]; nacc = __dadd_rn(nacc, __dmul_rn(v, v)); }
                 s.nr[threadIdx.x] = nacc;
             }
+            // a thread whose four query rows all lie beyond the row count has nothing to accumulate (the fallback for a
+            // few rows runs 64-row tiles with one or two live rows: 15 of 16 threads skip the FP64 work)
+            if (q0 + tq * 4 < nq_total)
             for (int kk = 0; kk < gn; ++kk) {
                 double xv[4], yv[4];
 #pragma unroll
